@@ -1,0 +1,56 @@
+/* ptb200_scenes.h — the scene DATA of the reference's three scene binaries, as C ABI loaders.
+ *
+ * In the reference a scene is OCaml code that builds closures (shirley_spheres/bin/main.ml:26-110,
+ * cornell-box/bin/main.ml:43-91,170-219, ganesha/bin/main.ml:30-119,205-260).  Here the same
+ * geometry/material tables are written into a ptb_scene (already in camera space) so the C++ CLI
+ * twins and the Python harness render exactly the same input; the getters let a checker read the
+ * tables back and feed them to another implementation.
+ */
+#ifndef PTB200_SCENES_H
+#define PTB200_SCENES_H
+#include "ptb200.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* shirley_spheres (main.ml:26-110,250-260): ground r=1000 checker, 3 big spheres, 23x23 jittered
+ * small spheres drawn from OCaml 5's Random (LXM) seeded with `seed` (the reference uses 42).
+ * cam[20] as ptb_camera_create.  The PRNG restatement is unverified against a real OCaml runtime
+ * (SURVEY.md App. C.1): the sphere list is input data shared by every implementation. */
+int ptb_scene_load_shirley(ptb_scene *, double aspect, int32_t seed, double cam[20]);
+
+/* cornell-box geometry (main.ml:43-91,170-219): 18 triangles + 3 spheres, camera eye (.5,.5,-1).
+ * The reference renders it with photon mapping only and has no background; `background_kind` /
+ * c0 / c1 are the caller's choice. */
+int ptb_scene_load_cornell(ptb_scene *, double aspect, int32_t background_kind, const double c0[3],
+                           const double c1[3], double cam[20]);
+
+/* ganesha assembly (ganesha/bin/main.ml:30-119,205-260) from an indexed mesh in WORLD space:
+ * camera eye (328,70.282,345)->(328,10,0) fov 30, all faces lambert (0.1,0.7,0.2) with tex
+ * (t00,t01,t11), plus the 10000x10000 checker floor (2 triangles) at the mesh's camera-space
+ * bbox-min y.  `xyz` = 3*nv floats (x,y,z interleaved, as a PLY vertex element stores them). */
+int ptb_scene_load_mesh(ptb_scene *, const float *xyz, int64_t n_vertices, const int32_t *faces,
+                        int64_t n_faces, double aspect, double cam[20]);
+
+/* Seeded synthetic stand-in for ganesha.ply (not in the repo): a displaced icosphere
+ * with about `target_faces` triangles placed where the ganesha mesh sits.  Writes up to the given
+ * capacities; returns counts through nv/nf. */
+int ptb_mesh_synthetic(int64_t target_faces, uint32_t seed, float *xyz, int64_t cap_vertices,
+                       int32_t *faces, int64_t cap_faces, int64_t *nv, int64_t *nf);
+
+/* table getters (sizes first with NULL buffers) */
+int ptb_scene_counts(const ptb_scene *, int64_t *n_spheres, int64_t *n_vertices,
+                     int64_t *n_triangles, int32_t *n_materials, int32_t *n_textures);
+int ptb_scene_get_spheres(const ptb_scene *, double *xs, double *ys, double *zs, double *rs,
+                          int32_t *material);
+int ptb_scene_get_triangles(const ptb_scene *, double *vx, double *vy, double *vz, int32_t *indices,
+                            int32_t *material, double *uv);
+int ptb_scene_get_materials(const ptb_scene *, ptb_material *, ptb_texture *);
+int ptb_scene_get_background(const ptb_scene *, int32_t *kind, double c0[3], double c1[3]);
+/* reference list order handed to Shape_tree.create: entry >= 0 sphere i, < 0 triangle ~entry */
+int ptb_scene_get_prim_order(const ptb_scene *, int32_t *order, int64_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

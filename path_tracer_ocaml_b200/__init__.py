@@ -1,0 +1,11 @@
+"""path_tracer_ocaml_b200 — host-side Python harness over libptb200 (C ABI + sm_100a CUDA kernels).
+
+The product is the shared library built from ``csrc/`` (see ``include/ptb200.h``).  This package only
+binds it with ctypes for the tests and ``bench.py``, and mirrors the reference's interface names
+(``Integrator.create/render``, ``Render_command.Args``, the scene binaries) so tests read like the
+reference's own.  There is no CPU fallback: importing works anywhere, but every compute call raises
+if the CUDA extension is missing or no GPU is present.
+"""
+from .capi import lib, PtbError, Params, Stats, Texture, Material  # noqa: F401
+from .scenes import Scene, shirley_spheres, cornell_box, synthetic_mesh_scene  # noqa: F401
+from .integrator import Integrator, Args  # noqa: F401

@@ -1,0 +1,235 @@
+// bvh.cpp — host-side tree construction for the device.
+//
+// Role in the reference: Shape_tree.Make(L).create (path_tracer/src/shape_tree.ml:252-263), a binary
+// binned-SAH tree with 32 bins whose leaves hold <=16 SoA spheres (Simd_leaf) or small arrays.
+// This is NOT that tree: the device wants few, fat, 128-bit-aligned nodes, so we build a binary
+// binned-SAH tree (our own cost model and termination) and collapse it into a 4-wide BVH laid out
+// breadth-first, so that the first K nodes are the top levels and can be staged in shared memory.
+// Spheres and triangles get separate subtrees joined under the root, which keeps every leaf
+// homogeneous (the reference's cornell `Shape` sum type, cornell-box/bin/main.ml:93-155, becomes a
+// type bit in the leaf code).  Closest-hit results do not depend on the tree shape.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <functional>
+#include <queue>
+
+#include "scene.hpp"
+
+namespace ptb {
+namespace {
+
+struct PrimRef {
+  Box box;
+  double c[3];
+  int32_t id;
+};
+
+struct BinNode {
+  Box box;
+  int lhs = -1, rhs = -1;  // children (binary inner)
+  int first = 0, count = 0, type = 0;  // leaf
+  bool leaf() const { return lhs < 0; }
+};
+
+constexpr int NBINS = 32;
+
+struct BinaryBuilder {
+  std::vector<PrimRef> &prims;
+  std::vector<BinNode> &nodes;
+  int type;
+  int base;  // offset of this type's slot range
+
+  int build(int lo, int hi) {
+    Box box;
+    box.reset();
+    Box cbox;
+    cbox.reset();
+    for (int i = lo; i < hi; ++i) {
+      box.grow(prims[i].box);
+      for (int a = 0; a < 3; ++a) {
+        cbox.mn[a] = std::min(cbox.mn[a], prims[i].c[a]);
+        cbox.mx[a] = std::max(cbox.mx[a], prims[i].c[a]);
+      }
+    }
+    int n = hi - lo;
+    int me = (int)nodes.size();
+    nodes.emplace_back();
+    nodes[me].box = box;
+    auto make_leaf = [&]() {
+      nodes[me].first = lo;
+      nodes[me].count = n;
+      nodes[me].type = type;
+      return me;
+    };
+    if (n <= LEAF_MAX && n <= 2) return make_leaf();
+    // binned SAH over the three axes
+    double best_cost = 1e300;
+    int best_axis = -1, best_split = -1;
+    for (int a = 0; a < 3; ++a) {
+      double ext = cbox.mx[a] - cbox.mn[a];
+      if (!(ext > 0.0)) continue;
+      double k = NBINS * (1.0 - 1e-9) / ext;
+      Box bb[NBINS];
+      int cnt[NBINS];
+      for (int b = 0; b < NBINS; ++b) bb[b].reset(), cnt[b] = 0;
+      for (int i = lo; i < hi; ++i) {
+        int b = (int)(k * (prims[i].c[a] - cbox.mn[a]));
+        b = std::min(std::max(b, 0), NBINS - 1);
+        bb[b].grow(prims[i].box);
+        cnt[b]++;
+      }
+      double right_area[NBINS];
+      int right_cnt[NBINS];
+      Box acc;
+      acc.reset();
+      int c = 0;
+      for (int b = NBINS - 1; b > 0; --b) {
+        acc.grow(bb[b]);
+        c += cnt[b];
+        right_area[b] = acc.area();
+        right_cnt[b] = c;
+      }
+      acc.reset();
+      c = 0;
+      for (int b = 0; b < NBINS - 1; ++b) {
+        acc.grow(bb[b]);
+        c += cnt[b];
+        if (c == 0 || right_cnt[b + 1] == 0) continue;
+        double cost = acc.area() * c + right_area[b + 1] * right_cnt[b + 1];
+        if (cost < best_cost) best_cost = cost, best_axis = a, best_split = b;
+      }
+    }
+    if (best_axis < 0) {
+      // all centroids coincide: split by index while the leaf is too big
+      if (n <= LEAF_MAX) return make_leaf();
+      int mid = lo + n / 2;
+      int l = build(lo, mid);
+      int r = build(mid, hi);
+      nodes[me].lhs = l, nodes[me].rhs = r;
+      return me;
+    }
+    if (n <= LEAF_MAX) {
+      // leaf cost n * Ci vs split cost Ct + sum; Ci = 1, Ct = 1.2 (a 4-wide node visit costs a few
+      // primitive tests on the device)
+      double split_cost = 1.2 + best_cost / std::max(box.area(), 1e-300);
+      if (split_cost >= (double)n) return make_leaf();
+    }
+    double ext = cbox.mx[best_axis] - cbox.mn[best_axis];
+    double k = NBINS * (1.0 - 1e-9) / ext;
+    auto mid_it = std::partition(prims.begin() + lo, prims.begin() + hi, [&](const PrimRef &p) {
+      int b = (int)(k * (p.c[best_axis] - cbox.mn[best_axis]));
+      b = std::min(std::max(b, 0), NBINS - 1);
+      return b <= best_split;
+    });
+    int mid = (int)(mid_it - prims.begin());
+    if (mid == lo || mid == hi) mid = lo + n / 2;
+    int l = build(lo, mid);
+    int r = build(mid, hi);
+    nodes[me].lhs = l, nodes[me].rhs = r;
+    return me;
+  }
+};
+
+}  // namespace
+
+void build_wide_bvh(const HostScene &s, WideBVH *out) {
+  out->nodes.clear();
+  out->sphere_order.clear();
+  out->tri_order.clear();
+  std::vector<BinNode> bn;
+  std::vector<PrimRef> sph((size_t)s.n_spheres()), tri((size_t)s.n_tris());
+  for (size_t i = 0; i < sph.size(); ++i) {
+    PrimRef &p = sph[i];
+    double c[3] = {s.sx[i], s.sy[i], s.sz[i]};
+    for (int a = 0; a < 3; ++a) p.box.mn[a] = c[a] - s.sr[i], p.box.mx[a] = c[a] + s.sr[i], p.c[a] = c[a];
+    p.id = (int32_t)i;
+  }
+  for (size_t i = 0; i < tri.size(); ++i) {
+    PrimRef &p = tri[i];
+    p.box.reset();
+    for (int k = 0; k < 3; ++k) {
+      int v = s.tidx[3 * i + k];
+      double c[3] = {s.vx[v], s.vy[v], s.vz[v]};
+      for (int a = 0; a < 3; ++a) {
+        p.box.mn[a] = std::min(p.box.mn[a], c[a]);
+        p.box.mx[a] = std::max(p.box.mx[a], c[a]);
+      }
+    }
+    for (int a = 0; a < 3; ++a) p.c[a] = 0.5 * (p.box.mn[a] + p.box.mx[a]);
+    p.id = (int32_t)i;
+  }
+  int sroot = -1, troot = -1;
+  if (!sph.empty()) {
+    BinaryBuilder b{sph, bn, 0, 0};
+    sroot = b.build(0, (int)sph.size());
+  }
+  if (!tri.empty()) {
+    BinaryBuilder b{tri, bn, 1, 0};
+    troot = b.build(0, (int)tri.size());
+  }
+  for (auto &p : sph) out->sphere_order.push_back(p.id);
+  for (auto &p : tri) out->tri_order.push_back(p.id);
+
+  // children of the (virtual) root
+  std::vector<int> top;
+  if (sroot >= 0) top.push_back(sroot);
+  if (troot >= 0) top.push_back(troot);
+
+  // collapse: BFS; each wide node gathers up to 4 binary descendants, always opening the inner
+  // candidate with the largest surface area.
+  struct Pending {
+    std::vector<int> seeds;  // binary nodes whose union this wide node covers
+    int depth;
+  };
+  std::queue<Pending> q;
+  q.push({top, 1});
+  int max_depth = 0;
+  // wide node index is assigned in BFS order = push order
+  std::vector<std::vector<int>> child_sets;
+  std::vector<int> node_depth;
+  while (!q.empty()) {
+    Pending cur = q.front();
+    q.pop();
+    std::vector<int> ch = cur.seeds;
+    // a single inner seed is opened unconditionally so that a wide node never has one inner child
+    for (;;) {
+      int pick = -1;
+      double pa = -1.0;
+      for (size_t i = 0; i < ch.size(); ++i)
+        if (!bn[ch[i]].leaf() && bn[ch[i]].box.area() > pa) pa = bn[ch[i]].box.area(), pick = (int)i;
+      if (pick < 0 || ch.size() >= 4) break;
+      int n = ch[pick];
+      ch[pick] = bn[n].lhs;
+      ch.push_back(bn[n].rhs);
+    }
+    child_sets.push_back(ch);
+    node_depth.push_back(cur.depth);
+    max_depth = std::max(max_depth, cur.depth);
+    for (int c : ch)
+      if (!bn[c].leaf()) q.push({{bn[c].lhs, bn[c].rhs}, cur.depth + 1});
+  }
+  // second pass: emit nodes; inner children get indices in the same BFS order
+  out->nodes.resize(child_sets.size());
+  int next_inner = 1;
+  for (size_t i = 0; i < child_sets.size(); ++i) {
+    WideNode &w = out->nodes[i];
+    for (int k = 0; k < 4; ++k) {
+      for (int a = 0; a < 3; ++a) w.mn[a][k] = 1e30, w.mx[a][k] = -1e30;
+      w.child[k] = EMPTY_CHILD;
+    }
+    const auto &ch = child_sets[i];
+    for (size_t k = 0; k < ch.size(); ++k) {
+      const BinNode &b = bn[ch[k]];
+      for (int a = 0; a < 3; ++a) w.mn[a][k] = b.box.mn[a], w.mx[a][k] = b.box.mx[a];
+      if (b.leaf())
+        w.child[k] = leaf_code(b.type, b.first, b.count);
+      else
+        w.child[k] = next_inner++;
+    }
+  }
+  out->depth = max_depth;
+  out->max_stack = 3 * max_depth + 2;
+}
+
+}  // namespace ptb

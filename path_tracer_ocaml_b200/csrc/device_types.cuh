@@ -1,0 +1,90 @@
+// device_types.cuh — device-side data layout of libptb200 (sm_100a).  Product code.
+//
+// Everything is templated on the arithmetic type R: float is the production path, double is the
+// validation mode (PTB_FLAG_F64) that runs the identical pipeline in the reference's precision.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ptb {
+
+constexpr int MAX_BOUNCES = 64;
+constexpr int MAX_DIMS = 2 + 2 * MAX_BOUNCES;
+constexpr int NUM_MAT_KINDS = 3;  // Lambertian, Metal, Dielectric (material.ml:3-9)
+
+// 128-bit aligned 4-vector; for double it is two 128-bit halves.
+template <class R>
+struct alignas(16) Vec4 {
+  R x, y, z, w;
+};
+template <class R>
+struct V3 {
+  R x, y, z;
+};
+
+// 4-wide BVH node, SoA over the four children: lo[axis][child], hi[axis][child], child[4].
+// float: 112 B = 7 x 16 B.  The stride is an ODD multiple of 16 B on purpose: lanes that visit
+// different nodes then spread over all eight 16-byte bank groups of shared memory instead of
+// colliding on one (a 128 B stride would be an 8-way conflict on every field).
+template <class R>
+struct alignas(16) Node4 {
+  R lo[3][4];
+  R hi[3][4];
+  int32_t child[4];
+};
+static_assert(sizeof(Node4<float>) == 112, "Node4<float> must be 7 x 16 bytes");
+static_assert(sizeof(Node4<double>) == 208, "Node4<double> must be 13 x 16 bytes");
+
+struct DMat {
+  int32_t kind;
+  int32_t tex;
+  double index;
+};
+template <class R>
+struct DTex {
+  int32_t kind, w, h, even, odd, pad;
+  R rgb[3];
+};
+
+template <class R>
+struct DScene {
+  const Node4<R> *nodes;
+  const Vec4<R> *spheres;  // (cx, cy, cz, r) per slot
+  const Vec4<R> *tris;     // 3 per slot: (v0,_), (e1,_), (e2,_)
+  const int32_t *sphere_id, *tri_id;    // slot -> caller index
+  const int32_t *sphere_mat, *tri_mat;  // slot -> material row
+  const R *tri_uv;                      // 6 per slot
+  const DMat *mats;
+  const DTex<R> *texs;
+  int32_t n_nodes, n_spheres, n_tris;
+  int32_t scene_in_smem;  // 1: nodes+spheres+tris are staged in shared memory by every block
+  int32_t stack_cap;      // traversal stack entries per thread
+  int32_t bg_kind;
+  R bg0[3], bg1[3];
+};
+
+// Wavefront queue entry = three Vec4 (48 B in float):
+//   ray queue : A = (origin, pixel)      B = (direction, R2 offset)   C = (attenuation, -)
+//   hit queue : A = (hit point, pixel)   B = (direction, R2 offset)   C = (attenuation, prim)
+template <class R>
+struct Queue {
+  Vec4<R> *A, *B, *C;
+};
+
+struct Ctl {
+  unsigned int n_rays[MAX_BOUNCES + 1];            // rays entering bounce b of the current batch
+  unsigned int n_mat[MAX_BOUNCES][4];              // hits per material kind at bounce b
+  unsigned long long rays_by_bounce[MAX_BOUNCES];  // accumulated over batches
+  unsigned long long total_rays;
+};
+
+struct RenderConst {
+  int32_t W, H, spp, max_bounces;
+  int32_t npix;  // pixels owned by this rank
+  int32_t pad;
+  double llx, lly, vx, vy;  // Camera.t (camera.ml:50-53)
+  double widthf, heightf;   // 1 // width, 1 // height (integrator.ml:92-93)
+  double alpha[MAX_DIMS];   // Low_discrepancy_sequence alpha table (host glibc pow)
+};
+
+}  // namespace ptb

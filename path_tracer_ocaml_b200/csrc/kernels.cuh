@@ -1,0 +1,641 @@
+// kernels.cuh — the wavefront pipeline of libptb200: hand-written CUDA for sm_100a.  Product code.
+//
+// Stages (BASELINE.json north_star):
+//   k_raygen   camera rays from the Roberts R2 sequence, evaluated on device in float64 with
+//              un-fused multiplies/adds so the sample stream is bit-identical to the reference
+//              (integrator.ml:98-105, low_discrepancy_sequence.ml:33-36, camera.ml:93-102)
+//   k_trace    closest-hit traversal of the 4-wide BVH (nodes + primitives staged in shared memory,
+//              per-thread stack in bank-conflict-free shared memory), ray-sphere and ray-triangle
+//              tests (sphere.ml:35-54 / lib.rs:102-178, triangle.ml:74-98); misses are shaded with
+//              the background and accumulated; hits are appended to per-material queues with
+//              __ballot_sync/__popc warp aggregation
+//   k_shade    per-material scatter (material.ml:22-57, shader_space.ml, pdf.ml); each warp works
+//              on one material's queue, survivors are compacted into the next ray queue
+//   k_resolve  3x3 binomial reconstruction filter + gamma (film_tile.ml:23-38, integrator.ml:114-128,
+//              152-154) over the per-pixel sample sums
+// No tensor cores: no stage is a dense contraction.
+#pragma once
+#include <cfloat>
+
+#include "device_types.cuh"
+
+namespace ptb {
+
+// ---------------------------------------------------------------------------------------------
+// scalar helpers, overloaded on float/double
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float r_sqrt(float x) { return sqrtf(x); }
+__device__ __forceinline__ double r_sqrt(double x) { return sqrt(x); }
+__device__ __forceinline__ float r_abs(float x) { return fabsf(x); }
+__device__ __forceinline__ double r_abs(double x) { return fabs(x); }
+__device__ __forceinline__ float r_min(float a, float b) { return fminf(a, b); }
+__device__ __forceinline__ double r_min(double a, double b) { return fmin(a, b); }
+__device__ __forceinline__ float r_max(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ double r_max(double a, double b) { return fmax(a, b); }
+__device__ __forceinline__ float r_fma(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ double r_fma(double a, double b, double c) { return fma(a, b, c); }
+__device__ __forceinline__ float r_copysign(float a, float b) { return copysignf(a, b); }
+__device__ __forceinline__ double r_copysign(double a, double b) { return copysign(a, b); }
+__device__ __forceinline__ void r_sincos2pi(float v, float *s, float *c) { sincospif(2.0f * v, s, c); }
+__device__ __forceinline__ void r_sincos2pi(double v, double *s, double *c) {
+  sincos(v * 2.0 * 3.141592653589793, s, c);  // shader_space.ml:59-61, same expression
+}
+__device__ __forceinline__ float r_pow5(float x) {
+  float x2 = x * x;
+  return x2 * x2 * x;
+}
+__device__ __forceinline__ double r_pow5(double x) { return pow(x, 5.0); }  // material.ml:19,37 `** 5.0`
+// 1/|v|: reference normalizes with 1/hypot(x, hypot(y, z)) (affine.ml:65-68)
+__device__ __forceinline__ float r_inv_len(float x, float y, float z) {
+  return rsqrtf(fmaf(x, x, fmaf(y, y, z * z)));
+}
+__device__ __forceinline__ double r_inv_len(double x, double y, double z) {
+  return 1.0 / hypot(x, hypot(y, z));
+}
+__device__ __forceinline__ float r_inv_len4(float r, float x, float y, float z) {
+  return rsqrtf(fmaf(r, r, fmaf(x, x, fmaf(y, y, z * z))));
+}
+__device__ __forceinline__ double r_inv_len4(double r, double x, double y, double z) {
+  return 1.0 / hypot(hypot(r, x), hypot(y, z));  // quaternion.ml:11-15
+}
+template <class R>
+struct Lim;
+template <>
+struct Lim<float> {
+  static __device__ __forceinline__ float inf() { return __int_as_float(0x7f800000); }
+  static __device__ __forceinline__ float tmax() { return FLT_MAX; }
+  static __device__ __forceinline__ float far_scale() { return 1.0000004f; }
+  static __device__ __forceinline__ float tiny() { return 1e-30f; }
+  static __device__ __forceinline__ float below_one() { return 0.99999994f; }
+};
+template <>
+struct Lim<double> {
+  static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+  static __device__ __forceinline__ double tmax() { return DBL_MAX; }  // Float.max_finite_value (main.ml:274)
+  static __device__ __forceinline__ double far_scale() { return 1.0 + 1e-15; }
+  static __device__ __forceinline__ double tiny() { return 1e-300; }
+  static __device__ __forceinline__ double below_one() { return 0.99999999999999989; }
+};
+__device__ __forceinline__ float i2r(int v, float) { return __int_as_float(v); }
+__device__ __forceinline__ double i2r(int v, double) { return __longlong_as_double((long long)v); }
+__device__ __forceinline__ int r2i(float v) { return __float_as_int(v); }
+__device__ __forceinline__ int r2i(double v) { return (int)__double_as_longlong(v); }
+
+template <class R>
+__device__ __forceinline__ V3<R> operator+(V3<R> a, V3<R> b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+template <class R>
+__device__ __forceinline__ V3<R> operator-(V3<R> a, V3<R> b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+template <class R>
+__device__ __forceinline__ V3<R> operator*(V3<R> a, R s) { return {a.x * s, a.y * s, a.z * s}; }
+template <class R>
+__device__ __forceinline__ V3<R> neg(V3<R> a) { return {-a.x, -a.y, -a.z}; }
+template <class R>
+__device__ __forceinline__ R dot(V3<R> a, V3<R> b) { return r_fma(a.x, b.x, r_fma(a.y, b.y, a.z * b.z)); }
+template <class R>
+__device__ __forceinline__ V3<R> cross(V3<R> p, V3<R> q) {
+  return {r_fma(p.y, q.z, -(p.z * q.y)), r_fma(p.z, q.x, -(p.x * q.z)), r_fma(p.x, q.y, -(p.y * q.x))};
+}
+template <class R>
+__device__ __forceinline__ V3<R> normalize(V3<R> v) { return v * r_inv_len(v.x, v.y, v.z); }
+
+// ---------------------------------------------------------------------------------------------
+// Roberts R2 sample (low_discrepancy_sequence.ml:19-20,33-36): frac(0.5 + alpha * float(1+offset)).
+// float64, explicitly un-fused so no FMA contraction can change a bit.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double r2_sample(double alpha, int offset) {
+  double x = __dadd_rn(0.5, __dmul_rn(alpha, (double)(1 + offset)));
+  return __dsub_rn(x, trunc(x));
+}
+
+// ---------------------------------------------------------------------------------------------
+// quaternion shading frame (shader_space.ml:11-32, quaternion.ml:25-42)
+// ---------------------------------------------------------------------------------------------
+template <class R>
+struct Quat {
+  R r;
+  V3<R> v;
+};
+template <class R>
+__device__ __forceinline__ Quat<R> quat_mul(Quat<R> a, Quat<R> b) {
+  R r = a.r * b.r - dot(a.v, b.v);
+  V3<R> v = (cross(a.v, b.v) + b.v * a.r) + a.v * b.r;
+  return {r, v};
+}
+template <class R>
+__device__ __forceinline__ V3<R> quat_transform(Quat<R> t, V3<R> v) {
+  Quat<R> tc = {t.r, neg(t.v)};
+  return quat_mul(quat_mul(t, Quat<R>{R(0), v}), tc).v;
+}
+template <class R>
+__device__ __forceinline__ Quat<R> frame_from_normal(V3<R> n) {
+  const R eps = sizeof(R) == 4 ? R(1e-7) : R(1e-9);  // shader_space.ml:9 uses 1e-9 (float64)
+  if (n.z > R(1) - eps) return {R(1), {R(0), R(0), R(0)}};
+  if (n.z < eps - R(1)) return {R(0), {R(0), R(1), R(0)}};
+  R r = R(1) + n.z, x = n.y, y = -n.x;
+  R s = r_inv_len4(r, x, y, R(0));
+  return {r * s, {x * s, y * s, R(0)}};
+}
+
+// ---------------------------------------------------------------------------------------------
+// primitive tests
+// ---------------------------------------------------------------------------------------------
+// Ray-sphere in the numerically robust form the reference uses (sphere.ml:35-54; lib.rs:130-166):
+// discriminant from the perpendicular offset, q = b' + sign(b')*sqrt(a*disc), t = c>0 ? c/q : q/a.
+template <class R>
+__device__ __forceinline__ void sphere_test(Vec4<R> s, V3<R> o, V3<R> d, R a, R inv_a, R tmin, R &tbest,
+                                            int &best, int id) {
+  V3<R> f = {s.x - o.x, s.y - o.y, s.z - o.z};
+  R r2 = s.w * s.w;
+  R bp = dot(f, d);
+  R boa = bp * inv_a;
+  V3<R> w = {r_fma(d.x, boa, -f.x), r_fma(d.y, boa, -f.y), r_fma(d.z, boa, -f.z)};
+  R disc = r2 - dot(w, w);
+  if (disc >= R(0)) {
+    R q = bp + r_copysign(r_sqrt(a * disc), bp);
+    R c = dot(f, f) - r2;
+    R t = (c > R(0)) ? c / q : q * inv_a;
+    if (t >= tmin && t <= tbest) {  // `<=`: a later equal t wins (lib.rs:171-176, shape_tree.ml:303-309)
+      tbest = t;
+      best = id;
+    }
+  }
+}
+// Moller-Trumbore, two-sided, |det| < 1e-6 rejected (triangle.ml:74-98)
+template <class R>
+__device__ __forceinline__ void tri_test(Vec4<R> v0, Vec4<R> e1v, Vec4<R> e2v, V3<R> o, V3<R> d, R tmin,
+                                         R &tbest, int &best, int id) {
+  V3<R> e1 = {e1v.x, e1v.y, e1v.z}, e2 = {e2v.x, e2v.y, e2v.z};
+  V3<R> pvec = cross(d, e2);
+  R det = dot(e1, pvec);
+  if (r_abs(det) < R(1e-6)) return;
+  R inv = R(1) / det;
+  V3<R> tvec = {o.x - v0.x, o.y - v0.y, o.z - v0.z};
+  R u = inv * dot(tvec, pvec);
+  V3<R> qvec = cross(tvec, e1);
+  R v = inv * dot(d, qvec);
+  if (u >= R(0) && u <= R(1) && v >= R(0) && u + v <= R(1)) {
+    R t = inv * dot(e2, qvec);
+    if (t >= tmin && t <= tbest) {
+      tbest = t;
+      best = id;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// BVH4 traversal.  `SMEM`: nodes/spheres/tris pointers address shared memory.
+// Stack entries live in shared memory as stack[level * blockDim + tid]: bank = tid % 32 for every
+// level, so pushes and pops never conflict whatever the per-lane depth.
+// ---------------------------------------------------------------------------------------------
+#define PTB_CSWAP(ta, ca, tb, cb)   \
+  {                                 \
+    bool sw_ = tb < ta;             \
+    R tt_ = sw_ ? ta : tb;          \
+    int cc_ = sw_ ? ca : cb;        \
+    ta = sw_ ? tb : ta;             \
+    ca = sw_ ? cb : ca;             \
+    tb = tt_;                       \
+    cb = cc_;                       \
+  }
+
+template <class R>
+__device__ __forceinline__ void traverse(const char *__restrict__ nodes, const Vec4<R> *__restrict__ spheres,
+                                         const Vec4<R> *__restrict__ tris, V3<R> o, V3<R> d, R tmin, R &tbest,
+                                         int &best, int *stk_ref, R *stk_t, int stk_stride, int stk_cap) {
+  const R INF = Lim<R>::inf();
+  auto safe_rcp = [](R x) {
+    return (r_abs(x) < Lim<R>::tiny()) ? r_copysign(R(1) / Lim<R>::tiny(), x) : R(1) / x;
+  };
+  const V3<R> idir = {safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z)};
+  const V3<R> oid = {o.x * idir.x, o.y * idir.y, o.z * idir.z};
+  // near/far plane arrays by direction sign: Vec4 index inside the node (lo = 0..2, hi = 3..5)
+  const int nx = d.x >= R(0) ? 0 : 3, ny = d.y >= R(0) ? 1 : 4, nz = d.z >= R(0) ? 2 : 5;
+  const int fx = 3 - nx, fy = 5 - ny, fz = 7 - nz;
+  const R a = dot(d, d);
+  const R inv_a = R(1) / a;
+  int sp = 0;
+  int cur = 0;
+  for (;;) {
+    if (cur >= 0) {
+      const Vec4<R> *n = reinterpret_cast<const Vec4<R> *>(nodes + (size_t)cur * sizeof(Node4<R>));
+      const Vec4<R> bnx = n[nx], bny = n[ny], bnz = n[nz], bfx = n[fx], bfy = n[fy], bfz = n[fz];
+      const int4 ch = *reinterpret_cast<const int4 *>(n + 6);
+      const R fs = Lim<R>::far_scale();
+#define PTB_SLAB(k)                                                                                  \
+  R tn##k = r_max(r_max(r_fma(bnx.k, idir.x, -oid.x), r_fma(bny.k, idir.y, -oid.y)),                 \
+                  r_max(r_fma(bnz.k, idir.z, -oid.z), tmin));                                        \
+  R tf##k = r_min(r_min(r_fma(bfx.k, idir.x, -oid.x), r_fma(bfy.k, idir.y, -oid.y)),                 \
+                  r_min(r_fma(bfz.k, idir.z, -oid.z), tbest)) * fs;                                  \
+  tn##k = (tn##k <= tf##k) ? tn##k : INF;
+      PTB_SLAB(x)
+      PTB_SLAB(y)
+      PTB_SLAB(z)
+      PTB_SLAB(w)
+#undef PTB_SLAB
+      int c0 = ch.x, c1 = ch.y, c2 = ch.z, c3 = ch.w;
+      R t0 = tnx, t1 = tny, t2 = tnz, t3 = tnw;
+      PTB_CSWAP(t0, c0, t1, c1)
+      PTB_CSWAP(t2, c2, t3, c3)
+      PTB_CSWAP(t0, c0, t2, c2)
+      PTB_CSWAP(t1, c1, t3, c3)
+      PTB_CSWAP(t1, c1, t2, c2)
+      if (t0 < INF) {
+        cur = c0;
+        if (t3 < INF && sp < stk_cap) {
+          stk_ref[sp * stk_stride] = c3;
+          stk_t[sp * stk_stride] = t3;
+          ++sp;
+        }
+        if (t2 < INF && sp < stk_cap) {
+          stk_ref[sp * stk_stride] = c2;
+          stk_t[sp * stk_stride] = t2;
+          ++sp;
+        }
+        if (t1 < INF && sp < stk_cap) {
+          stk_ref[sp * stk_stride] = c1;
+          stk_t[sp * stk_stride] = t1;
+          ++sp;
+        }
+        continue;
+      }
+    } else {
+      const unsigned code = ~(unsigned)cur;
+      const int first = (int)(code & 0x3FFFFFFu);
+      const int cnt = (int)((code >> 26) & 15u) + 1;
+      if (((code >> 30) & 1u) == 0u) {
+        for (int i = 0; i < cnt; ++i)
+          sphere_test<R>(spheres[first + i], o, d, a, inv_a, tmin, tbest, best, first + i);
+      } else {
+        for (int i = 0; i < cnt; ++i) {
+          const Vec4<R> *t = tris + 3 * (size_t)(first + i);
+          tri_test<R>(t[0], t[1], t[2], o, d, tmin, tbest, best, (first + i) | (1 << 30));
+        }
+      }
+    }
+    // pop, skipping subtrees that start beyond the current best hit
+    for (;;) {
+      if (sp == 0) return;
+      --sp;
+      cur = stk_ref[sp * stk_stride];
+      if (stk_t[sp * stk_stride] <= tbest) break;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// textures (texture.ml:16-31) and backgrounds (shirley main.ml:104-110)
+// ---------------------------------------------------------------------------------------------
+template <class R>
+__device__ __forceinline__ V3<R> tex_eval(const DTex<R> *__restrict__ texs, int t, R u, R v) {
+  DTex<R> T = texs[t];
+  if (T.kind == PTB_TEX_CHECKER) {
+    R xp = u * R(T.w - 1), yp = v * R(T.h - 1);
+    int px = ((int)xp) & 1, py = ((int)yp) & 1;  // Float.to_int truncates toward zero
+    T = texs[px == py ? T.even : T.odd];
+  }
+  return {T.rgb[0], T.rgb[1], T.rgb[2]};
+}
+template <class R>
+__device__ __forceinline__ V3<R> background(const DScene<R> &sc, V3<R> d) {
+  if (sc.bg_kind == PTB_BG_CONSTANT) return {sc.bg0[0], sc.bg0[1], sc.bg0[2]};
+  V3<R> dn = normalize(d);
+  R t = R(0.5) * (dn.y + R(1));
+  R s = R(1) - t;
+  return {sc.bg0[0] * s + sc.bg1[0] * t, sc.bg0[1] * s + sc.bg1[1] * t, sc.bg0[2] * s + sc.bg1[2] * t};
+}
+
+// =================================================================================================
+// kernels
+// =================================================================================================
+
+// Stage 1 — camera rays.  One thread per sample of the batch [first, first+n) of this rank's
+// enumeration (pass-major over the rank's pixel list, which is in tile order).
+template <class R>
+__global__ void __launch_bounds__(256) k_raygen(RenderConst rc, const int32_t *__restrict__ pixel_list, int pass0,
+                                                int i0, unsigned n, Queue<R> out, double *__restrict__ dbg_cx,
+                                                double *__restrict__ dbg_cy) {
+  for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    long long idx = (long long)i0 + k;
+    int pass = pass0 + (int)(idx / rc.npix);
+    int i = (int)(idx % rc.npix);
+    int pixel = pixel_list[i];
+    int gy = pixel / rc.W, gx = pixel - gy * rc.W;
+    int offset = pixel + pass * rc.spp;  // integrator.ml:98 (sic: pass * samples_per_pixel)
+    double dx = r2_sample(rc.alpha[0], offset), dy = r2_sample(rc.alpha[1], offset);
+    double cx = __dmul_rn(__dadd_rn((double)gx, dx), rc.widthf);                    // integrator.ml:104
+    double cy = __dsub_rn(1.0, __dmul_rn(__dadd_rn((double)gy, dy), rc.heightf));   // integrator.ml:105
+    if (dbg_cx) dbg_cx[k] = cx;
+    if (dbg_cy) dbg_cy[k] = cy;
+    double ddx = __dadd_rn(rc.llx, __dmul_rn(rc.vx, cx));  // camera.ml:96-97
+    double ddy = __dadd_rn(rc.lly, __dmul_rn(rc.vy, cy));
+    V3<R> dir = normalize(V3<R>{R(ddx), R(ddy), R(-1)});
+    out.A[k] = {R(0), R(0), R(0), i2r(pixel, R())};
+    out.B[k] = {dir.x, dir.y, dir.z, i2r(offset, R())};
+    out.C[k] = {R(1), R(1), R(1), R(0)};
+  }
+}
+
+// Stage 2+3 — traversal and primitive tests.
+// MODE 0: pipeline (miss -> background into sums; hit -> per-material queue)
+// MODE 1: intersect only (t and caller primitive index per ray)
+template <class R, int MODE>
+__global__ void __launch_bounds__(256)
+    k_trace(DScene<R> sc, Queue<R> rays, const unsigned *__restrict__ n_ptr, unsigned n_imm, Queue<R> q0,
+            Queue<R> q1, Queue<R> q2, unsigned *__restrict__ n_mat, int enqueue_hits, R *__restrict__ sums,
+            R tmin_arg, R tmax_arg, R *__restrict__ out_t, int32_t *__restrict__ out_prim) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const unsigned n = n_ptr ? *n_ptr : n_imm;
+  const int tid = threadIdx.x;
+  const char *nodes = reinterpret_cast<const char *>(sc.nodes);
+  const Vec4<R> *spheres = sc.spheres;
+  const Vec4<R> *tris = sc.tris;
+  size_t scene_bytes = 0;
+  if (sc.scene_in_smem) {
+    const size_t nb = (size_t)sc.n_nodes * sizeof(Node4<R>);
+    const size_t sb = (size_t)sc.n_spheres * sizeof(Vec4<R>);
+    const size_t tb = (size_t)sc.n_tris * 3 * sizeof(Vec4<R>);
+    scene_bytes = nb + sb + tb;
+    if (blockIdx.x * blockDim.x < n) {  // blocks without work skip the staging copy
+      int4 *dst = reinterpret_cast<int4 *>(smem);
+      const int4 *s0 = reinterpret_cast<const int4 *>(sc.nodes);
+      const int4 *s1 = reinterpret_cast<const int4 *>(sc.spheres);
+      const int4 *s2 = reinterpret_cast<const int4 *>(sc.tris);
+      for (size_t i = tid; i < nb / 16; i += blockDim.x) dst[i] = s0[i];
+      for (size_t i = tid; i < sb / 16; i += blockDim.x) dst[nb / 16 + i] = s1[i];
+      for (size_t i = tid; i < tb / 16; i += blockDim.x) dst[(nb + sb) / 16 + i] = s2[i];
+    }
+    nodes = reinterpret_cast<const char *>(smem);
+    spheres = reinterpret_cast<const Vec4<R> *>(smem + nb);
+    tris = reinterpret_cast<const Vec4<R> *>(smem + nb + sb);
+    __syncthreads();
+  }
+  int *stk_ref = reinterpret_cast<int *>(smem + scene_bytes) + tid;
+  R *stk_t = reinterpret_cast<R *>(smem + scene_bytes + (size_t)sc.stack_cap * blockDim.x * sizeof(int)) + tid;
+  const unsigned lane = tid & 31;
+
+  for (unsigned base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+    const unsigned i = base + tid;
+    const bool valid = i < n;
+    Vec4<R> A = {R(0), R(0), R(0), R(0)}, B = {R(0), R(0), R(1), R(0)};
+    if (valid) {
+      A = rays.A[i];
+      B = rays.B[i];
+    }
+    const V3<R> o = {A.x, A.y, A.z}, d = {B.x, B.y, B.z};
+    R tbest = (MODE == 0) ? Lim<R>::tmax() : tmax_arg;
+    const R tmin = (MODE == 0) ? R(0) : tmin_arg;
+    int best = -1;
+    if (valid) traverse<R>(nodes, spheres, tris, o, d, tmin, tbest, best, stk_ref, stk_t, blockDim.x, sc.stack_cap);
+
+    if (MODE == 1) {
+      if (valid) {
+        int slot = best & 0x3FFFFFFF;
+        int prim = best < 0 ? -1 : ((best >> 30) & 1 ? sc.n_spheres + sc.tri_id[slot] : sc.sphere_id[slot]);
+        out_t[i] = best < 0 ? R(NAN) : tbest;
+        out_prim[i] = prim;
+      }
+      continue;
+    }
+    // ---- pipeline epilogue -------------------------------------------------------------------
+    int kind = -1;  // material kind of the hit, -1 = miss / nothing to enqueue
+    if (valid) {
+      if (best < 0) {
+        // integrator.ml:36: emit0 + attn0 * background ray  (emit0 == 0: Material.emit is black)
+        const Vec4<R> C = rays.C[i];
+        const V3<R> bg = background(sc, d);
+        const int pixel = r2i(A.w);
+        atomicAdd(&sums[3 * (size_t)pixel + 0], C.x * bg.x);
+        atomicAdd(&sums[3 * (size_t)pixel + 1], C.y * bg.y);
+        atomicAdd(&sums[3 * (size_t)pixel + 2], C.z * bg.z);
+      } else if (enqueue_hits) {
+        const int slot = best & 0x3FFFFFFF;
+        const int m = (best >> 30) & 1 ? sc.tri_mat[slot] : sc.sphere_mat[slot];
+        kind = sc.mats[m].kind;
+      }
+    }
+    // per-material queues, warp-aggregated append
+#pragma unroll
+    for (int m = 0; m < NUM_MAT_KINDS; ++m) {
+      const unsigned mask = __ballot_sync(0xffffffffu, kind == m);
+      if (mask == 0u) continue;
+      unsigned slot0 = 0;
+      if (lane == (unsigned)(__ffs(mask) - 1)) slot0 = atomicAdd(&n_mat[m], (unsigned)__popc(mask));
+      slot0 = __shfl_sync(0xffffffffu, slot0, __ffs(mask) - 1);
+      if (kind == m) {
+        const unsigned dst = slot0 + (unsigned)__popc(mask & ((1u << lane) - 1u));
+        const Queue<R> &q = (m == 0) ? q0 : (m == 1 ? q1 : q2);
+        const Vec4<R> C = rays.C[i];
+        q.A[dst] = {r_fma(tbest, d.x, o.x), r_fma(tbest, d.y, o.y), r_fma(tbest, d.z, o.z), A.w};
+        q.B[dst] = B;
+        q.C[dst] = {C.x, C.y, C.z, i2r(best, R())};
+      }
+    }
+  }
+}
+
+// Stage 4 — material scatter.  Work item = one warp-sized chunk of ONE material's hit queue, so the
+// material switch below is warp-uniform.
+template <class R>
+__global__ void __launch_bounds__(256)
+    k_shade(DScene<R> sc, RenderConst rc, int bounce, Queue<R> q0, Queue<R> q1, Queue<R> q2,
+            const unsigned *__restrict__ n_mat, Queue<R> out, unsigned *__restrict__ n_out) {
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned n0 = n_mat[0], n1 = n_mat[1], n2 = n_mat[2];
+  const unsigned c0 = (n0 + 31) >> 5, c1 = (n1 + 31) >> 5, c2 = (n2 + 31) >> 5;
+  const unsigned total = c0 + c1 + c2;
+  const unsigned warps = (gridDim.x * blockDim.x) >> 5;
+  const int j = 2 + 2 * bounce;  // take_2d cursor (integrator.ml:20-28): every hit so far took two
+  const double alpha_u = rc.alpha[j], alpha_v = rc.alpha[j + 1];
+  for (unsigned w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total; w += warps) {
+    int m;
+    unsigned i, nm;
+    if (w < c0) m = 0, i = w * 32 + lane, nm = n0;
+    else if (w < c0 + c1) m = 1, i = (w - c0) * 32 + lane, nm = n1;
+    else m = 2, i = (w - c0 - c1) * 32 + lane, nm = n2;
+    const Queue<R> &q = (m == 0) ? q0 : (m == 1 ? q1 : q2);
+    const bool valid = i < nm;
+    bool alive = false;
+    V3<R> no = {R(0), R(0), R(0)}, nd = {R(0), R(0), R(1)}, nattn = {R(0), R(0), R(0)};
+    Vec4<R> A = {R(0), R(0), R(0), R(0)}, B = A;
+    if (valid) {
+      A = q.A[i];
+      B = q.B[i];
+      const Vec4<R> C = q.C[i];
+      V3<R> p = {A.x, A.y, A.z};
+      const V3<R> d = {B.x, B.y, B.z};
+      const int offset = r2i(B.w);
+      const int best = r2i(C.w);
+      const int slot = best & 0x3FFFFFFF;
+      const bool is_tri = (best >> 30) & 1;
+      // geometric normal (sphere.ml:21 / triangle.ml:18-23)
+      V3<R> n;
+      Vec4<R> v0 = {R(0), R(0), R(0), R(0)}, e1 = v0, e2 = v0;
+      if (!is_tri) {
+        const Vec4<R> s = sc.spheres[slot];
+        n = normalize(V3<R>{p.x - s.x, p.y - s.y, p.z - s.z});
+        if (sizeof(R) == 4) p = {r_fma(n.x, s.w, s.x), r_fma(n.y, s.w, s.y), r_fma(n.z, s.w, s.z)};
+      } else {
+        v0 = sc.tris[3 * (size_t)slot], e1 = sc.tris[3 * (size_t)slot + 1], e2 = sc.tris[3 * (size_t)slot + 2];
+        n = normalize(cross(V3<R>{e1.x, e1.y, e1.z}, V3<R>{e2.x, e2.y, e2.z}));
+      }
+      const bool front = dot(d, n) < R(0);  // sphere.ml:60 / triangle.ml:56
+      if (!front) n = neg(n);
+      const Quat<R> frame = frame_from_normal(n);              // Shader_space.create
+      const V3<R> wi = quat_transform(frame, neg(d));           // Shader_space.omega_i
+      const Quat<R> frame_inv = {frame.r, neg(frame.v)};
+      const int mrow = is_tri ? sc.tri_mat[slot] : sc.sphere_mat[slot];
+      const DMat mat = sc.mats[mrow];
+      const double ud = r2_sample(alpha_u, offset), vd = r2_sample(alpha_v, offset);
+      V3<R> albedo = {R(1), R(1), R(1)};
+      if (m != PTB_MAT_DIELECTRIC) {
+        const DTex<R> T = sc.texs[mat.tex];
+        if (T.kind == PTB_TEX_SOLID) {
+          albedo = {T.rgb[0], T.rgb[1], T.rgb[2]};
+        } else {
+          R tu, tv;
+          if (!is_tri) {  // Sphere.tex_coord (sphere.ml:25-33) on the (flipped) normal
+            const R PI = R(3.141592653589793);
+            R theta, phi;
+            if (sizeof(R) == 4) {
+              theta = atan2f(sqrtf(fmaf((float)n.x, (float)n.x, (float)n.z * (float)n.z)), -(float)n.y);
+              phi = PI + atan2f(-(float)n.z, (float)n.x);
+            } else {
+              theta = acos(-(double)n.y);
+              phi = PI + atan2(-(double)n.z, (double)n.x);
+            }
+            tu = phi * (R(1) / (R(2) * PI));
+            tv = theta * (R(1) / PI);
+          } else {  // barycentric mix of the three tex coords (triangle.ml:49-54)
+            const V3<R> a1 = {e1.x, e1.y, e1.z}, a2 = {e2.x, e2.y, e2.z}, a3 = {p.x - v0.x, p.y - v0.y, p.z - v0.z};
+            R d00 = dot(a1, a1), d01 = dot(a1, a2), d11 = dot(a2, a2), d20 = dot(a3, a1), d21 = dot(a3, a2);
+            R inv = R(1) / (d00 * d11 - d01 * d01);
+            R bu = (d11 * d20 - d01 * d21) * inv, bv = (d00 * d21 - d01 * d20) * inv, bw = R(1) - bu - bv;
+            const R *uv = sc.tri_uv + 6 * (size_t)slot;
+            tu = uv[0] * bw + uv[2] * bu + uv[4] * bv;
+            tv = uv[1] * bw + uv[3] * bu + uv[5] * bv;
+          }
+          albedo = tex_eval(sc.texs, mat.tex, tu, tv);
+        }
+      }
+      const V3<R> attn0 = {C.x, C.y, C.z};
+      V3<R> dir_ss = {R(0), R(0), R(1)};
+      if (m == PTB_MAT_LAMBERTIAN) {
+        // Scatter.Diffuse; Pdf.sample = cosine hemisphere (pdf.ml:5-9, shader_space.ml:56-64);
+        // diffuse_pd / divisor == 1 exactly, diffuse_pd = 0 iff z = 0 (integrator.ml:48-58)
+        R u = r_min(R(ud), Lim<R>::below_one()), sn, cs;
+        R rr = r_sqrt(u);
+        r_sincos2pi(R(vd), &sn, &cs);
+        dir_ss = {rr * cs, rr * sn, r_sqrt(R(1) - u)};
+        alive = dir_ss.z > R(0);
+        nattn = {albedo.x * attn0.x, albedo.y * attn0.y, albedo.z * attn0.z};
+      } else if (m == PTB_MAT_METAL) {
+        // material.ml:28-44: mirror, Schlick-tinted; omega_r.z <= 0 -> Absorb
+        dir_ss = {-wi.x, -wi.y, wi.z};
+        alive = wi.z > R(0);
+        R s5 = r_pow5(R(1) - wi.z);
+        V3<R> att = {albedo.x + (R(1) - albedo.x) * s5, albedo.y + (R(1) - albedo.y) * s5,
+                     albedo.z + (R(1) - albedo.z) * s5};
+        nattn = {att.x * attn0.x, att.y * attn0.y, att.z * attn0.z};
+      } else {
+        // material.ml:45-57: Dielectric; reflect on TIR or schlick > u, else refract
+        R c = r_min(r_max(wi.z, R(0)), R(1));
+        R s = r_sqrt(R(1) - c * c);
+        R ratio = front ? R(1.0 / mat.index) : R(mat.index);
+        R q0_ = (R(1) - ratio) / (R(1) + ratio);
+        R r0 = q0_ * q0_;
+        R sch = r0 + (R(1) - r0) * r_pow5(R(1) - c);
+        if (ratio * s > R(1) || sch > R(ud)) {
+          dir_ss = {-wi.x, -wi.y, wi.z};
+        } else {  // Shader_space.refract (shader_space.ml:41-49)
+          R cc = r_min(wi.z, R(1));
+          V3<R> perp = {(R(0) - wi.x) * ratio, (R(0) - wi.y) * ratio, (cc - wi.z) * ratio};
+          dir_ss = {perp.x, perp.y, perp.z - r_sqrt(r_abs(R(1) - dot(perp, perp)))};
+        }
+        alive = true;
+        nattn = attn0;  // Color.white
+      }
+      // Shader_space.world_ray (shader_space.ml:51-54)
+      nd = quat_transform(frame_inv, dir_ss);
+      no = {r_fma(nd.x, R(1e-3), p.x), r_fma(nd.y, R(1e-3), p.y), r_fma(nd.z, R(1e-3), p.z)};
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, alive);
+    if (mask) {
+      unsigned slot0 = 0;
+      const int leader = __ffs(mask) - 1;
+      if ((int)lane == leader) slot0 = atomicAdd(n_out, (unsigned)__popc(mask));
+      slot0 = __shfl_sync(0xffffffffu, slot0, leader);
+      if (alive) {
+        const unsigned dst = slot0 + (unsigned)__popc(mask & ((1u << lane) - 1u));
+        out.A[dst] = {no.x, no.y, no.z, A.w};
+        out.B[dst] = {nd.x, nd.y, nd.z, B.w};
+        out.C[dst] = {nattn.x, nattn.y, nattn.z, R(0)};
+      }
+    }
+  }
+}
+
+// batch bookkeeping: fold the finished batch's ray counts into the totals, reset the counters and
+// publish the next batch's size.
+__global__ void k_batch_ctl(Ctl *ctl, unsigned next_n) {
+  const int t = threadIdx.x;
+  if (t < MAX_BOUNCES) {
+    unsigned v = ctl->n_rays[t];
+    ctl->rays_by_bounce[t] += v;
+    if (v) atomicAdd(&ctl->total_rays, (unsigned long long)v);
+  }
+  __syncthreads();
+  if (t <= MAX_BOUNCES) ctl->n_rays[t] = (t == 0) ? next_n : 0u;
+  if (t < MAX_BOUNCES) {
+    ctl->n_mat[t][0] = ctl->n_mat[t][1] = ctl->n_mat[t][2] = ctl->n_mat[t][3] = 0u;
+  }
+}
+
+// Stage 5 — reconstruction filter + gamma.  out[X,Y] = sum_d w(d) * S[X-dx, Y-dy] over sources inside
+// the image (film_tile.ml:23-38 splats, integrator.ml:114-128 drops destinations outside the image),
+// then sqrt(x * 1/spp) (integrator.ml:152-154).
+template <class R, class OUT>
+__global__ void __launch_bounds__(256) k_resolve(const R *__restrict__ sums, OUT *__restrict__ out, int W, int H,
+                                                 double spp_inv, int flags, double w00, double w01, double w02,
+                                                 double w10, double w11, double w12, double w20, double w21,
+                                                 double w22) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= W * H) return;
+  const int y = p / W, x = p - y * W;
+  double acc[3] = {0, 0, 0};
+  if (flags & PTB_FLAG_NO_FILTER) {
+    for (int c = 0; c < 3; ++c) acc[c] = (double)sums[3 * (size_t)p + c];
+  } else {
+    const double wt[3][3] = {{w00, w01, w02}, {w10, w11, w12}, {w20, w21, w22}};
+    for (int dy = -1; dy <= 1; ++dy)
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int sx = x - dx, sy = y - dy;
+        if (sx < 0 || sx >= W || sy < 0 || sy >= H) continue;
+        const double wgt = wt[dy + 1][dx + 1];
+        const R *s = sums + 3 * ((size_t)sy * W + sx);
+        for (int c = 0; c < 3; ++c) acc[c] = fma(wgt, (double)s[c], acc[c]);
+      }
+  }
+  const bool raw = flags & (PTB_FLAG_RAW_SUMS | PTB_FLAG_NO_FILTER);
+  for (int c = 0; c < 3; ++c) out[3 * (size_t)p + c] = (OUT)(raw ? acc[c] : sqrt(acc[c] * spp_inv));
+}
+
+// R2 stream dump: out[i*D + d] = get(offsets[i], d), through the SAME device function as the pipeline
+__global__ void k_r2_stream(RenderConst rc, int D, const int32_t *__restrict__ offsets, long long n,
+                            double *__restrict__ out) {
+  long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n * D) return;
+  long long i = k / D;
+  int dim = (int)(k - i * D);
+  out[k] = r2_sample(rc.alpha[dim], offsets[i]);
+}
+
+// user rays (3 floats each) -> ray queue
+template <class R>
+__global__ void k_pack_rays(const float *__restrict__ o, const float *__restrict__ d, long long n, Queue<R> q) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  q.A[i] = {R(o[3 * i]), R(o[3 * i + 1]), R(o[3 * i + 2]), R(0)};
+  q.B[i] = {R(d[3 * i]), R(d[3 * i + 1]), R(d[3 * i + 2]), R(0)};
+}
+
+}  // namespace ptb

@@ -1,0 +1,705 @@
+// render.cu — device state, launch orchestration and the compute entry points of the C ABI.
+// Product code: nothing from oracle/, no CPU fallback (every entry point needs a CUDA device).
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "handle.hpp"
+#include "kernels.cuh"
+
+namespace ptb {
+
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(PTB_E_CUDA, std::string(#call) + " failed: " + cudaGetErrorString(e_));     \
+  } while (0)
+
+template <class R>
+struct Tables {
+  Node4<R> *nodes = nullptr;
+  Vec4<R> *spheres = nullptr, *tris = nullptr;
+  R *tri_uv = nullptr;
+  DTex<R> *texs = nullptr;
+  bool ready = false;
+};
+template <class R>
+struct Work {
+  Queue<R> rays{nullptr, nullptr, nullptr};
+  Queue<R> mq[NUM_MAT_KINDS]{};
+  size_t cap = 0;
+};
+
+struct DeviceState {
+  int device = -1;
+  int sm_count = 0;
+  size_t smem_optin = 0;
+  int32_t *sphere_id = nullptr, *tri_id = nullptr, *sphere_mat = nullptr, *tri_mat = nullptr;
+  DMat *mats = nullptr;
+  Tables<float> tf;
+  Tables<double> td;
+  Work<float> wf;
+  Work<double> wd;
+  Ctl *ctl = nullptr;
+  int32_t *pixel_list = nullptr;
+  std::vector<int32_t> pixel_list_host;
+  int pl_W = 0, pl_H = 0, pl_rank = -1, pl_world = 0, npix = 0;
+  template <class R>
+  Tables<R> &tables();
+  template <class R>
+  Work<R> &work();
+};
+template <>
+Tables<float> &DeviceState::tables<float>() { return tf; }
+template <>
+Tables<double> &DeviceState::tables<double>() { return td; }
+template <>
+Work<float> &DeviceState::work<float>() { return wf; }
+template <>
+Work<double> &DeviceState::work<double>() { return wd; }
+
+template <class R>
+static void free_tables(Tables<R> &t) {
+  cudaFree(t.nodes), cudaFree(t.spheres), cudaFree(t.tris), cudaFree(t.tri_uv), cudaFree(t.texs);
+  t = Tables<R>();
+}
+template <class R>
+static void free_queue(Queue<R> &q) {
+  cudaFree(q.A), cudaFree(q.B), cudaFree(q.C);
+  q = Queue<R>{nullptr, nullptr, nullptr};
+}
+template <class R>
+static void free_work(Work<R> &w) {
+  free_queue(w.rays);
+  for (auto &q : w.mq) free_queue(q);
+  w.cap = 0;
+}
+void destroy_device_state(DeviceState *d) {
+  if (!d) return;
+  if (d->device >= 0) cudaSetDevice(d->device);
+  cudaFree(d->sphere_id), cudaFree(d->tri_id), cudaFree(d->sphere_mat), cudaFree(d->tri_mat);
+  cudaFree(d->mats), cudaFree(d->ctl), cudaFree(d->pixel_list);
+  free_tables(d->tf), free_tables(d->td);
+  free_work(d->wf), free_work(d->wd);
+  delete d;
+}
+
+static int check_device(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(PTB_E_NO_DEVICE, std::string("no CUDA device: libptb200 has no CPU path (") +
+                                     (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") + ")");
+  if (device < 0 || device >= n) return fail(PTB_E_INVALID, "device ordinal out of range");
+  CK(cudaSetDevice(device));
+  return PTB_OK;
+}
+
+template <class T>
+static int upload(T **dst, const std::vector<T> &src) {
+  *dst = nullptr;
+  size_t bytes = std::max<size_t>(src.size(), 1) * sizeof(T);
+  CK(cudaMalloc((void **)dst, bytes));
+  if (!src.empty()) CK(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return PTB_OK;
+}
+
+// conservative narrowing of box planes: the float box must contain the float primitives
+template <class R>
+static R box_lo(double x, double ext);
+template <class R>
+static R box_hi(double x, double ext);
+template <>
+double box_lo<double>(double x, double) { return x; }
+template <>
+double box_hi<double>(double x, double) { return x; }
+template <>
+float box_lo<float>(double x, double ext) {
+  if (x > 1e29) return 1e30f;
+  float f = (float)(x - 4e-7 * (std::fabs(x) + ext));
+  return std::nextafterf(f, -INFINITY);
+}
+template <>
+float box_hi<float>(double x, double ext) {
+  if (x < -1e29) return -1e30f;
+  float f = (float)(x + 4e-7 * (std::fabs(x) + ext));
+  return std::nextafterf(f, INFINITY);
+}
+
+template <class R>
+static int ensure_tables(ptb_scene *s) {
+  DeviceState *d = s->dev;
+  Tables<R> &t = d->tables<R>();
+  if (t.ready) return PTB_OK;
+  const HostScene &h = s->host;
+  const WideBVH &b = s->bvh;
+  std::vector<Node4<R>> nodes(b.nodes.size());
+  for (size_t i = 0; i < nodes.size(); ++i) {
+    for (int k = 0; k < 4; ++k) {
+      double ext = 0;
+      for (int a = 0; a < 3; ++a) ext = std::max(ext, b.nodes[i].mx[a][k] - b.nodes[i].mn[a][k]);
+      for (int a = 0; a < 3; ++a) {
+        nodes[i].lo[a][k] = box_lo<R>(b.nodes[i].mn[a][k], ext);
+        nodes[i].hi[a][k] = box_hi<R>(b.nodes[i].mx[a][k], ext);
+      }
+      nodes[i].child[k] = b.nodes[i].child[k];
+    }
+  }
+  std::vector<Vec4<R>> sph(b.sphere_order.size());
+  for (size_t k = 0; k < sph.size(); ++k) {
+    int i = b.sphere_order[k];
+    sph[k] = {(R)h.sx[i], (R)h.sy[i], (R)h.sz[i], (R)h.sr[i]};
+  }
+  std::vector<Vec4<R>> tri(3 * b.tri_order.size());
+  std::vector<R> uv(6 * b.tri_order.size());
+  for (size_t k = 0; k < b.tri_order.size(); ++k) {
+    int i = b.tri_order[k];
+    int ia = h.tidx[3 * i], ib = h.tidx[3 * i + 1], ic = h.tidx[3 * i + 2];
+    tri[3 * k + 0] = {(R)h.vx[ia], (R)h.vy[ia], (R)h.vz[ia], R(0)};
+    tri[3 * k + 1] = {(R)(h.vx[ib] - h.vx[ia]), (R)(h.vy[ib] - h.vy[ia]), (R)(h.vz[ib] - h.vz[ia]), R(0)};
+    tri[3 * k + 2] = {(R)(h.vx[ic] - h.vx[ia]), (R)(h.vy[ic] - h.vy[ia]), (R)(h.vz[ic] - h.vz[ia]), R(0)};
+    for (int c = 0; c < 6; ++c) uv[6 * k + c] = (R)h.tuv[6 * i + c];
+  }
+  std::vector<DTex<R>> texs(h.tex.size());
+  for (size_t i = 0; i < texs.size(); ++i) {
+    const ptb_texture &x = h.tex[i];
+    texs[i] = {x.kind, x.width, x.height, x.even, x.odd, 0, {(R)x.rgb[0], (R)x.rgb[1], (R)x.rgb[2]}};
+  }
+  int rc;
+  if ((rc = upload(&t.nodes, nodes))) return rc;
+  if ((rc = upload(&t.spheres, sph))) return rc;
+  if ((rc = upload(&t.tris, tri))) return rc;
+  if ((rc = upload(&t.tri_uv, uv))) return rc;
+  if ((rc = upload(&t.texs, texs))) return rc;
+  t.ready = true;
+  return PTB_OK;
+}
+
+template <class R>
+static int ensure_work(DeviceState *d, size_t cap) {
+  Work<R> &w = d->work<R>();
+  if (w.cap >= cap) return PTB_OK;
+  free_work(w);
+  auto alloc_q = [&](Queue<R> &q) -> int {
+    CK(cudaMalloc((void **)&q.A, cap * sizeof(Vec4<R>)));
+    CK(cudaMalloc((void **)&q.B, cap * sizeof(Vec4<R>)));
+    CK(cudaMalloc((void **)&q.C, cap * sizeof(Vec4<R>)));
+    return PTB_OK;
+  };
+  int rc;
+  if ((rc = alloc_q(w.rays))) return rc;
+  for (auto &q : w.mq)
+    if ((rc = alloc_q(q))) return rc;
+  w.cap = cap;
+  return PTB_OK;
+}
+
+// this rank's pixels, in the reference's tile order (Tile.split ~max_area:1024, integrator.ml:132-133;
+// tile t belongs to rank t mod world), row-major inside a tile like Tile.iter (tile.ml:71-79)
+static int ensure_pixel_list(DeviceState *d, int W, int H, int rank, int world) {
+  if (d->pixel_list && d->pl_W == W && d->pl_H == H && d->pl_rank == rank && d->pl_world == world) return PTB_OK;
+  std::vector<TileRect> tiles;
+  tile_split(W, H, 32 * 32, &tiles);
+  std::vector<int32_t> &pl = d->pixel_list_host;
+  pl.clear();
+  for (size_t t = 0; t < tiles.size(); ++t) {
+    if ((int)(t % (size_t)world) != rank) continue;
+    const TileRect &r = tiles[t];
+    for (int y = 0; y < r.h; ++y)
+      for (int x = 0; x < r.w; ++x) pl.push_back((r.row + y) * W + (r.col + x));
+  }
+  cudaFree(d->pixel_list);
+  d->pixel_list = nullptr;
+  int rc = upload(&d->pixel_list, pl);
+  if (rc) return rc;
+  d->pl_W = W, d->pl_H = H, d->pl_rank = rank, d->pl_world = world, d->npix = (int)pl.size();
+  return PTB_OK;
+}
+
+static int fill_render_const(const ptb_params &p, int npix, RenderConst *rc) {
+  if (p.width <= 0 || p.height <= 0 || p.samples_per_pixel <= 0)
+    return fail(PTB_E_INVALID, "render: width, height and samples_per_pixel must be positive");
+  if (p.max_bounces < 0 || p.max_bounces > MAX_BOUNCES)
+    return fail(PTB_E_INVALID, "render: max_bounces must be in [0, 64]");
+  if ((long long)p.width * p.height + (long long)p.samples_per_pixel * p.samples_per_pixel >= (1LL << 31))
+    return fail(PTB_E_INVALID, "render: sample offset would overflow int32");
+  std::memset(rc, 0, sizeof *rc);
+  rc->W = p.width, rc->H = p.height, rc->spp = p.samples_per_pixel, rc->max_bounces = p.max_bounces;
+  rc->npix = npix;
+  rc->llx = p.lower_left_x, rc->lly = p.lower_left_y, rc->vx = p.view_x, rc->vy = p.view_y;
+  rc->widthf = 1.0 / (double)p.width;
+  rc->heightf = 1.0 / (double)p.height;
+  lds_alpha(2 + 2 * p.max_bounces, rc->alpha);  // Integrator.create_sampler (integrator.ml:89)
+  return PTB_OK;
+}
+
+template <class R>
+static DScene<R> make_dscene(ptb_scene *s, size_t *scene_bytes_out) {
+  DeviceState *d = s->dev;
+  Tables<R> &t = d->tables<R>();
+  DScene<R> sc;
+  std::memset(&sc, 0, sizeof sc);
+  sc.nodes = t.nodes, sc.spheres = t.spheres, sc.tris = t.tris;
+  sc.sphere_id = d->sphere_id, sc.tri_id = d->tri_id, sc.sphere_mat = d->sphere_mat, sc.tri_mat = d->tri_mat;
+  sc.tri_uv = t.tri_uv, sc.mats = d->mats, sc.texs = t.texs;
+  sc.n_nodes = (int)s->bvh.nodes.size();
+  sc.n_spheres = (int)s->bvh.sphere_order.size();
+  sc.n_tris = (int)s->bvh.tri_order.size();
+  size_t bytes = (size_t)sc.n_nodes * sizeof(Node4<R>) + (size_t)sc.n_spheres * sizeof(Vec4<R>) +
+                 (size_t)sc.n_tris * 3 * sizeof(Vec4<R>);
+  sc.scene_in_smem = bytes <= 100 * 1024 ? 1 : 0;
+  sc.stack_cap = std::min(std::max(s->bvh.max_stack, 8), 96);
+  sc.bg_kind = s->host.bg_kind;
+  for (int i = 0; i < 3; ++i) sc.bg0[i] = (R)s->host.bg0[i], sc.bg1[i] = (R)s->host.bg1[i];
+  *scene_bytes_out = sc.scene_in_smem ? bytes : 0;
+  return sc;
+}
+
+struct TraceLaunch {
+  int block = 256, grid = 0;
+  size_t smem = 0;
+};
+template <class R, int MODE>
+static int trace_config(DeviceState *d, const DScene<R> &sc, size_t scene_bytes, TraceLaunch *tl) {
+  tl->block = 256;
+  for (;;) {
+    tl->smem = scene_bytes + (size_t)sc.stack_cap * tl->block * (sizeof(int) + sizeof(R));
+    if (tl->smem <= d->smem_optin || tl->block == 64) break;
+    tl->block /= 2;
+  }
+  if (tl->smem > d->smem_optin) return fail(PTB_E_NOMEM, "trace: scene + stack do not fit shared memory");
+  CK(cudaFuncSetAttribute(k_trace<R, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl->smem));
+  int per_sm = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<R, MODE>, tl->block, tl->smem));
+  if (per_sm < 1) return fail(PTB_E_CUDA, "trace: kernel cannot be resident");
+  tl->grid = d->sm_count * per_sm;
+  return PTB_OK;
+}
+
+static size_t batch_capacity() {
+  size_t nb = (size_t)1 << 22;
+  if (const char *e = std::getenv("PTB_BATCH")) {
+    long long v = std::atoll(e);
+    if (v >= 1024) nb = (size_t)v;
+  }
+  return nb;
+}
+
+// The wavefront loop: raygen, then per bounce trace -> shade, batch after batch, all asynchronous on
+// `st`.  Adds into d_sums (R[3*W*H]).
+template <class R>
+static int render_impl(ptb_scene *s, const ptb_params &p, R *d_sums, cudaStream_t st, ptb_stats *stats) {
+  DeviceState *d = s->dev;
+  int rc;
+  if ((rc = ensure_tables<R>(s))) return rc;
+  int world = p.tile_world > 0 ? p.tile_world : 1;
+  if (p.tile_rank < 0 || p.tile_rank >= world) return fail(PTB_E_INVALID, "render: tile_rank out of range");
+  if ((rc = ensure_pixel_list(d, p.width, p.height, p.tile_rank, world))) return rc;
+  RenderConst rcst;
+  if ((rc = fill_render_const(p, d->npix, &rcst))) return rc;
+  const long long total = (long long)d->npix * p.samples_per_pixel;
+  const size_t NB = std::min<size_t>(batch_capacity(), (size_t)std::max<long long>(total, 1));
+  if ((rc = ensure_work<R>(d, NB))) return rc;
+  Work<R> &w = d->work<R>();
+  size_t scene_bytes = 0;
+  DScene<R> sc = make_dscene<R>(s, &scene_bytes);
+  TraceLaunch tl;
+  if ((rc = trace_config<R, 0>(d, sc, scene_bytes, &tl))) return rc;
+  const bool profile = (p.flags & PTB_FLAG_PROFILE) != 0;
+  std::vector<cudaEvent_t> tev;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  CK(cudaMemsetAsync(d->ctl, 0, sizeof(Ctl), st));
+  CK(cudaEventRecord(e0, st));
+  uint64_t launches = 0;
+  const int shade_grid = d->sm_count * 4;
+  for (long long first = 0; first < total; first += (long long)NB) {
+    const unsigned n = (unsigned)std::min<long long>((long long)NB, total - first);
+    k_batch_ctl<<<1, 128, 0, st>>>(d->ctl, n);
+    const int pass0 = (int)(first / d->npix), i0 = (int)(first % d->npix);
+    const int rg_grid = (int)std::min<long long>(((long long)n + 255) / 256, (long long)d->sm_count * 8);
+    k_raygen<R><<<rg_grid, 256, 0, st>>>(rcst, d->pixel_list, pass0, i0, n, w.rays, nullptr, nullptr);
+    launches += 2;
+    for (int b = 0; b < p.max_bounces; ++b) {
+      const bool last = (b == p.max_bounces - 1);
+      if (profile) {
+        cudaEvent_t a, z;
+        CK(cudaEventCreate(&a));
+        CK(cudaEventCreate(&z));
+        CK(cudaEventRecord(a, st));
+        tev.push_back(a);
+        tev.push_back(z);
+      }
+      k_trace<R, 0><<<tl.grid, tl.block, tl.smem, st>>>(sc, w.rays, &d->ctl->n_rays[b], 0u, w.mq[0], w.mq[1],
+                                                        w.mq[2], &d->ctl->n_mat[b][0], last ? 0 : 1, d_sums,
+                                                        R(0), R(0), nullptr, nullptr);
+      if (profile) CK(cudaEventRecord(tev.back(), st));
+      ++launches;
+      if (!last) {
+        // a path that is still alive after the last allowed bounce contributes black
+        // (integrator.ml:31-32), so the last bounce needs no scatter
+        k_shade<R><<<shade_grid, 256, 0, st>>>(sc, rcst, b, w.mq[0], w.mq[1], w.mq[2], &d->ctl->n_mat[b][0], w.rays,
+                                               &d->ctl->n_rays[b + 1]);
+        ++launches;
+      }
+    }
+  }
+  k_batch_ctl<<<1, 128, 0, st>>>(d->ctl, 0u);
+  ++launches;
+  CK(cudaEventRecord(e1, st));
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(st));
+  if (stats) {
+    Ctl host;
+    CK(cudaMemcpy(&host, d->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost));
+    stats->paths = (uint64_t)total;
+    stats->rays = host.total_rays;
+    for (int b = 0; b < MAX_BOUNCES; ++b) stats->rays_by_bounce[b] = host.rays_by_bounce[b];
+    stats->kernel_launches += launches;
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    stats->ms_device = ms;
+    double tr = 0;
+    for (size_t i = 0; i + 1 < tev.size(); i += 2) {
+      float m = 0;
+      CK(cudaEventElapsedTime(&m, tev[i], tev[i + 1]));
+      tr += m;
+    }
+    stats->ms_trace = tr;
+  }
+  for (cudaEvent_t e : tev) cudaEventDestroy(e);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return PTB_OK;
+}
+
+template <class R, class OUT>
+static int resolve_impl(const R *d_sums, OUT *d_out, int W, int H, int spp, int flags, cudaStream_t st) {
+  std::vector<double> w;
+  filter_binomial(5, 1, &w);  // integrator.ml:134-135
+  const int n = W * H;
+  k_resolve<R, OUT><<<(n + 255) / 256, 256, 0, st>>>(d_sums, d_out, W, H, 1.0 / (double)spp, flags, w[0], w[1],
+                                                      w[2], w[3], w[4], w[5], w[6], w[7], w[8]);
+  CK(cudaGetLastError());
+  return PTB_OK;
+}
+
+template <class R>
+static int render_host_impl(ptb_scene *s, const ptb_params &p, double *image, ptb_stats *stats) {
+  using clk = std::chrono::steady_clock;
+  const size_t n3 = (size_t)p.width * p.height * 3;
+  R *d_sums = nullptr;
+  double *d_img = nullptr;
+  CK(cudaMalloc((void **)&d_sums, n3 * sizeof(R)));
+  CK(cudaMalloc((void **)&d_img, n3 * sizeof(double)));
+  CK(cudaMemsetAsync(d_sums, 0, n3 * sizeof(R), 0));
+  int rc = render_impl<R>(s, p, d_sums, 0, stats);
+  if (!rc) rc = resolve_impl<R, double>(d_sums, d_img, p.width, p.height, p.samples_per_pixel, p.flags, 0);
+  if (!rc) {
+    auto t0 = clk::now();
+    cudaError_t e = cudaMemcpy(image, d_img, n3 * sizeof(double), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = fail(PTB_E_CUDA, std::string("image copy failed: ") + cudaGetErrorString(e));
+    if (stats) {
+      stats->ms_d2h = std::chrono::duration<double, std::milli>(clk::now() - t0).count();
+      stats->d2h_bytes = n3 * sizeof(double);
+      stats->kernel_launches += 1;
+    }
+  }
+  cudaFree(d_sums);
+  cudaFree(d_img);
+  return rc;
+}
+
+static int require_committed(ptb_scene *s, int device) {
+  if (!s) return fail(PTB_E_INVALID, "null scene");
+  if (!s->committed || !s->dev) return fail(PTB_E_STATE, "scene is not committed (call ptb_scene_commit)");
+  if (s->dev->device != device) return fail(PTB_E_STATE, "scene was committed on a different device");
+  return check_device(device);
+}
+
+}  // namespace ptb
+
+using namespace ptb;
+
+extern "C" {
+
+int ptb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int ptb_scene_commit(ptb_scene *s, int32_t device, double *ms) {
+  using clk = std::chrono::steady_clock;
+  if (!s) return fail(PTB_E_INVALID, "commit: null scene");
+  const HostScene &h = s->host;
+  // Shape_tree.create: `failwith "expected non-empty list of shapes"` (shape_tree.ml:254-255)
+  if (h.n_spheres() + h.n_tris() == 0) return fail(PTB_E_INVALID, "commit: expected non-empty list of shapes");
+  if (h.n_spheres() >= (1 << 26) || h.n_tris() >= (1 << 26)) return fail(PTB_E_INVALID, "commit: too many primitives");
+  auto bad_mat = [&](const std::vector<int32_t> &m) {
+    for (int32_t v : m)
+      if (v < 0 || v >= (int32_t)h.mat.size()) return true;
+    return false;
+  };
+  if (bad_mat(h.smat) || bad_mat(h.tmat)) return fail(PTB_E_INVALID, "commit: material row out of range");
+  for (const ptb_material &m : h.mat)
+    if (m.kind != PTB_MAT_DIELECTRIC && (m.texture < 0 || m.texture >= (int32_t)h.tex.size()))
+      return fail(PTB_E_INVALID, "commit: texture row out of range");
+  int rc = check_device(device);
+  if (rc) return rc;
+  auto t0 = clk::now();
+  build_wide_bvh(h, &s->bvh);
+  if (s->dev) destroy_device_state(s->dev);
+  s->dev = new DeviceState();
+  DeviceState *d = s->dev;
+  d->device = device;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  d->sm_count = prop.multiProcessorCount;
+  d->smem_optin = prop.sharedMemPerBlockOptin;
+  std::vector<int32_t> smat(s->bvh.sphere_order.size()), tmat(s->bvh.tri_order.size());
+  for (size_t k = 0; k < smat.size(); ++k) smat[k] = h.smat[s->bvh.sphere_order[k]];
+  for (size_t k = 0; k < tmat.size(); ++k) tmat[k] = h.tmat[s->bvh.tri_order[k]];
+  std::vector<DMat> mats(h.mat.size());
+  for (size_t i = 0; i < mats.size(); ++i) mats[i] = {h.mat[i].kind, h.mat[i].texture, h.mat[i].index};
+  if ((rc = upload(&d->sphere_id, s->bvh.sphere_order))) return rc;
+  if ((rc = upload(&d->tri_id, s->bvh.tri_order))) return rc;
+  if ((rc = upload(&d->sphere_mat, smat))) return rc;
+  if ((rc = upload(&d->tri_mat, tmat))) return rc;
+  if ((rc = upload(&d->mats, mats))) return rc;
+  CK(cudaMalloc((void **)&d->ctl, sizeof(Ctl)));
+  CK(cudaMemset(d->ctl, 0, sizeof(Ctl)));
+  s->committed = true;
+  if ((rc = ensure_tables<float>(s))) return rc;
+  CK(cudaDeviceSynchronize());
+  if (ms) *ms = std::chrono::duration<double, std::milli>(clk::now() - t0).count();
+  return PTB_OK;
+}
+
+int ptb_render(ptb_scene *s, const ptb_params *p, double *image, ptb_stats *stats) {
+  using clk = std::chrono::steady_clock;
+  if (!p || !image) return fail(PTB_E_INVALID, "render: null argument");
+  int rc = require_committed(s, p->device);
+  if (rc) return rc;
+  if (stats) std::memset(stats, 0, sizeof *stats);
+  auto t0 = clk::now();
+  rc = (p->flags & PTB_FLAG_F64) ? render_host_impl<double>(s, *p, image, stats)
+                                 : render_host_impl<float>(s, *p, image, stats);
+  if (stats) stats->ms_total = std::chrono::duration<double, std::milli>(clk::now() - t0).count();
+  return rc;
+}
+
+int ptb_render_device(ptb_scene *s, const ptb_params *p, float *d_sums, void *stream, ptb_stats *stats) {
+  using clk = std::chrono::steady_clock;
+  if (!p || !d_sums) return fail(PTB_E_INVALID, "render_device: null argument");
+  if (p->flags & PTB_FLAG_F64) return fail(PTB_E_INVALID, "render_device: float32 sums only");
+  int rc = require_committed(s, p->device);
+  if (rc) return rc;
+  if (stats) std::memset(stats, 0, sizeof *stats);
+  auto t0 = clk::now();
+  rc = render_impl<float>(s, *p, d_sums, (cudaStream_t)stream, stats);
+  if (stats) stats->ms_total = std::chrono::duration<double, std::milli>(clk::now() - t0).count();
+  return rc;
+}
+
+int ptb_resolve_device(const float *d_sums, float *d_image, int32_t width, int32_t height, int32_t spp,
+                       int32_t flags, int32_t device, void *stream) {
+  if (!d_sums || !d_image || width <= 0 || height <= 0 || spp <= 0) return fail(PTB_E_INVALID, "resolve: bad args");
+  int rc = check_device(device);
+  if (rc) return rc;
+  return resolve_impl<float, float>(d_sums, d_image, width, height, spp, flags, (cudaStream_t)stream);
+}
+
+int ptb_intersect_batch_device(ptb_scene *s, const float *d_o, const float *d_d, float t_min, float t_max,
+                               int64_t n, float *d_t, int32_t *d_prim, int32_t device, void *stream,
+                               ptb_stats *stats) {
+  if (!d_o || !d_d || !d_t || !d_prim || n < 0) return fail(PTB_E_INVALID, "intersect_batch: bad args");
+  int rc = require_committed(s, device);
+  if (rc) return rc;
+  DeviceState *d = s->dev;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t cap = std::min<size_t>(batch_capacity() * 4, (size_t)std::max<int64_t>(n, 1));
+  if ((rc = ensure_work<float>(d, cap))) return rc;
+  Work<float> &w = d->work<float>();
+  size_t scene_bytes = 0;
+  DScene<float> sc = make_dscene<float>(s, &scene_bytes);
+  TraceLaunch tl;
+  if ((rc = trace_config<float, 1>(d, sc, scene_bytes, &tl))) return rc;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  CK(cudaEventRecord(e0, st));
+  uint64_t launches = 0;
+  for (int64_t first = 0; first < n; first += (int64_t)cap) {
+    const long long m = std::min<int64_t>((int64_t)cap, n - first);
+    k_pack_rays<float><<<(unsigned)((m + 255) / 256), 256, 0, st>>>(d_o + 3 * first, d_d + 3 * first, m, w.rays);
+    k_trace<float, 1><<<tl.grid, tl.block, tl.smem, st>>>(sc, w.rays, nullptr, (unsigned)m, w.mq[0], w.mq[1], w.mq[2],
+                                                          nullptr, 0, nullptr, t_min, t_max, d_t + first,
+                                                          d_prim + first);
+    launches += 2;
+  }
+  CK(cudaEventRecord(e1, st));
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(st));
+  if (stats) {
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    stats->ms_device = ms;
+    stats->rays = (uint64_t)n;
+    stats->kernel_launches += launches;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return PTB_OK;
+}
+
+int ptb_intersect_batch(ptb_scene *s, const float *o, const float *dd, float t_min, float t_max, int64_t n,
+                        float *t_hit, int32_t *prim, int32_t device, ptb_stats *stats) {
+  using clk = std::chrono::steady_clock;
+  if (!o || !dd || !t_hit || !prim || n < 0) return fail(PTB_E_INVALID, "intersect_batch: bad args");
+  int rc = require_committed(s, device);
+  if (rc) return rc;
+  if (stats) std::memset(stats, 0, sizeof *stats);
+  auto t0 = clk::now();
+  float *d_o = nullptr, *d_d = nullptr, *d_t = nullptr;
+  int32_t *d_p = nullptr;
+  const size_t nn = (size_t)std::max<int64_t>(n, 1);
+  CK(cudaMalloc((void **)&d_o, nn * 12));
+  CK(cudaMalloc((void **)&d_d, nn * 12));
+  CK(cudaMalloc((void **)&d_t, nn * 4));
+  CK(cudaMalloc((void **)&d_p, nn * 4));
+  auto th = clk::now();
+  CK(cudaMemcpy(d_o, o, (size_t)n * 12, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_d, dd, (size_t)n * 12, cudaMemcpyHostToDevice));
+  double ms_h2d = std::chrono::duration<double, std::milli>(clk::now() - th).count();
+  rc = ptb_intersect_batch_device(s, d_o, d_d, t_min, t_max, n, d_t, d_p, device, nullptr, stats);
+  auto td = clk::now();
+  if (!rc) {
+    CK(cudaMemcpy(t_hit, d_t, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(prim, d_p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  }
+  cudaFree(d_o), cudaFree(d_d), cudaFree(d_t), cudaFree(d_p);
+  if (stats) {
+    stats->ms_h2d = ms_h2d;
+    stats->ms_d2h = std::chrono::duration<double, std::milli>(clk::now() - td).count();
+    stats->h2d_bytes = (uint64_t)n * 24;
+    stats->d2h_bytes = (uint64_t)n * 8;
+    stats->ms_total = std::chrono::duration<double, std::milli>(clk::now() - t0).count();
+  }
+  return rc;
+}
+
+int ptb_r2_stream(int32_t max_bounces, const int32_t *offsets, int64_t n, double *out, int32_t device) {
+  if (!offsets || !out || n < 0 || max_bounces < 0 || max_bounces > MAX_BOUNCES)
+    return fail(PTB_E_INVALID, "r2_stream: bad args");
+  int rc = check_device(device);
+  if (rc) return rc;
+  RenderConst rcst;
+  std::memset(&rcst, 0, sizeof rcst);
+  const int D = 2 + 2 * max_bounces;
+  lds_alpha(D, rcst.alpha);
+  int32_t *d_off = nullptr;
+  double *d_out = nullptr;
+  const size_t nn = (size_t)std::max<int64_t>(n, 1);
+  CK(cudaMalloc((void **)&d_off, nn * 4));
+  CK(cudaMalloc((void **)&d_out, nn * D * 8));
+  CK(cudaMemcpy(d_off, offsets, (size_t)n * 4, cudaMemcpyHostToDevice));
+  const long long total = (long long)n * D;
+  if (total > 0) k_r2_stream<<<(unsigned)((total + 255) / 256), 256>>>(rcst, D, d_off, n, d_out);
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(out, d_out, (size_t)n * D * 8, cudaMemcpyDeviceToHost));
+  cudaFree(d_off), cudaFree(d_out);
+  return PTB_OK;
+}
+
+int ptb_raygen(const ptb_params *p, int64_t first, int64_t n, int32_t *pixel, int32_t *offset, double *cx,
+               double *cy, float *dir_xyz) {
+  if (!p || n < 0 || first < 0) return fail(PTB_E_INVALID, "raygen: bad args");
+  int rc = check_device(p->device);
+  if (rc) return rc;
+  DeviceState tmp;  // scratch state: raygen needs no scene
+  int world = p->tile_world > 0 ? p->tile_world : 1;
+  if ((rc = ensure_pixel_list(&tmp, p->width, p->height, p->tile_rank, world))) return rc;
+  RenderConst rcst;
+  if ((rc = fill_render_const(*p, tmp.npix, &rcst))) {
+    cudaFree(tmp.pixel_list);
+    return rc;
+  }
+  const long long total = (long long)tmp.npix * p->samples_per_pixel;
+  if (first + n > total) {
+    cudaFree(tmp.pixel_list);
+    return fail(PTB_E_INVALID, "raygen: sample range exceeds W*H*spp of this rank");
+  }
+  const size_t nn = (size_t)std::max<int64_t>(n, 1);
+  Queue<float> q;
+  double *d_cx = nullptr, *d_cy = nullptr;
+  CK(cudaMalloc((void **)&q.A, nn * 16));
+  CK(cudaMalloc((void **)&q.B, nn * 16));
+  CK(cudaMalloc((void **)&q.C, nn * 16));
+  CK(cudaMalloc((void **)&d_cx, nn * 8));
+  CK(cudaMalloc((void **)&d_cy, nn * 8));
+  if (n > 0) {
+    const int pass0 = (int)(first / tmp.npix), i0 = (int)(first % tmp.npix);
+    k_raygen<float><<<(unsigned)((n + 255) / 256), 256>>>(rcst, tmp.pixel_list, pass0, i0, (unsigned)n, q, d_cx, d_cy);
+  }
+  CK(cudaGetLastError());
+  std::vector<Vec4<float>> A(nn), B(nn);
+  CK(cudaMemcpy(A.data(), q.A, (size_t)n * 16, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(B.data(), q.B, (size_t)n * 16, cudaMemcpyDeviceToHost));
+  if (cx) CK(cudaMemcpy(cx, d_cx, (size_t)n * 8, cudaMemcpyDeviceToHost));
+  if (cy) CK(cudaMemcpy(cy, d_cy, (size_t)n * 8, cudaMemcpyDeviceToHost));
+  for (int64_t i = 0; i < n; ++i) {
+    int32_t pi, oi;
+    std::memcpy(&pi, &A[i].w, 4);
+    std::memcpy(&oi, &B[i].w, 4);
+    if (pixel) pixel[i] = pi;
+    if (offset) offset[i] = oi;
+    if (dir_xyz) dir_xyz[3 * i] = B[i].x, dir_xyz[3 * i + 1] = B[i].y, dir_xyz[3 * i + 2] = B[i].z;
+  }
+  cudaFree(q.A), cudaFree(q.B), cudaFree(q.C), cudaFree(d_cx), cudaFree(d_cy), cudaFree(tmp.pixel_list);
+  return PTB_OK;
+}
+
+int ptb_first_hit(ptb_scene *s, const ptb_params *p, float *t_hit, int32_t *prim) {
+  if (!p || !t_hit || !prim) return fail(PTB_E_INVALID, "first_hit: null argument");
+  int rc = require_committed(s, p->device);
+  if (rc) return rc;
+  DeviceState *d = s->dev;
+  if ((rc = ensure_pixel_list(d, p->width, p->height, 0, 1))) return rc;
+  RenderConst rcst;
+  if ((rc = fill_render_const(*p, d->npix, &rcst))) return rc;
+  const size_t n = (size_t)d->npix;
+  if ((rc = ensure_work<float>(d, n))) return rc;
+  Work<float> &w = d->work<float>();
+  size_t scene_bytes = 0;
+  DScene<float> sc = make_dscene<float>(s, &scene_bytes);
+  TraceLaunch tl;
+  if ((rc = trace_config<float, 1>(d, sc, scene_bytes, &tl))) return rc;
+  float *d_t = nullptr;
+  int32_t *d_p = nullptr;
+  CK(cudaMalloc((void **)&d_t, n * 4));
+  CK(cudaMalloc((void **)&d_p, n * 4));
+  k_raygen<float><<<(unsigned)((n + 255) / 256), 256>>>(rcst, d->pixel_list, 0, 0, (unsigned)n, w.rays, nullptr, nullptr);
+  k_trace<float, 1><<<tl.grid, tl.block, tl.smem>>>(sc, w.rays, nullptr, (unsigned)n, w.mq[0], w.mq[1], w.mq[2], nullptr,
+                                                    0, nullptr, 0.0f, FLT_MAX, d_t, d_p);
+  CK(cudaGetLastError());
+  std::vector<float> ht(n);
+  std::vector<int32_t> hp(n);
+  CK(cudaMemcpy(ht.data(), d_t, n * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(hp.data(), d_p, n * 4, cudaMemcpyDeviceToHost));
+  cudaFree(d_t), cudaFree(d_p);
+  for (size_t k = 0; k < n; ++k) {
+    int px = d->pixel_list_host[k];
+    t_hit[px] = ht[k];
+    prim[px] = hp[k];
+  }
+  return PTB_OK;
+}
+
+}  // extern "C"
