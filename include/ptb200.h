@@ -172,6 +172,10 @@ int ptb_raygen(const ptb_params *, int64_t first, int64_t n, int32_t *pixel, int
  * traversal kernels): t (NaN on miss) and primitive index per pixel. */
 int ptb_first_hit(ptb_scene *, const ptb_params *, float *t_hit, int32_t *prim);
 
+/* Measures this device's FP32 FFMA issue rate (the roofline denominator SURVEY.md §8d asks for):
+ * 1e12 lane-operations/s, one FFMA on one lane = one lane-op.  Diagnostic, not on the render path. */
+int ptb_fp32_peak(int32_t device, double *tera_lane_ops, double *ms);
+
 /* Host-side helpers that mirror small reference functions the callers need. */
 /* Low_discrepancy_sequence.create (low_discrepancy_sequence.ml:8-31): alpha[0..dimension). */
 int ptb_lds_alpha(int32_t dimension, double *alpha);

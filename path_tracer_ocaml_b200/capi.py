@@ -66,6 +66,7 @@ SYMBOLS = {
     "ptb_r2_stream": (C.c_int, [C.c_int32, _ip, C.c_int64, _dp, C.c_int32]),
     "ptb_raygen": (C.c_int, [_P(Params), C.c_int64, C.c_int64, _ip, _ip, _dp, _dp, _fp]),
     "ptb_first_hit": (C.c_int, [_vp, _P(Params), _fp, _ip]),
+    "ptb_fp32_peak": (C.c_int, [C.c_int32, _dp, _dp]),
     "ptb_lds_alpha": (C.c_int, [C.c_int32, _dp]),
     "ptb_tile_split": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _ip, _ip, _ip, _ip, C.c_int32]),
     "ptb_filter_binomial": (C.c_int, [C.c_int32, C.c_int32, _dp]),

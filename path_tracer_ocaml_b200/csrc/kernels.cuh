@@ -576,9 +576,9 @@ __global__ void __launch_bounds__(256)
 
 // batch bookkeeping: fold the finished batch's ray counts into the totals, reset the counters and
 // publish the next batch's size.
-__global__ void k_batch_ctl(Ctl *ctl, unsigned next_n) {
+__global__ void k_batch_ctl(Ctl *ctl, unsigned next_n, int max_bounces) {
   const int t = threadIdx.x;
-  if (t < MAX_BOUNCES) {
+  if (t < max_bounces) {  // only bounces that were actually traced (integrator.ml:31-32)
     unsigned v = ctl->n_rays[t];
     ctl->rays_by_bounce[t] += v;
     if (v) atomicAdd(&ctl->total_rays, (unsigned long long)v);
@@ -627,6 +627,21 @@ __global__ void k_r2_stream(RenderConst rc, int D, const int32_t *__restrict__ o
   long long i = k / D;
   int dim = (int)(k - i * D);
   out[k] = r2_sample(rc.alpha[dim], offsets[i]);
+}
+
+// FP32 issue-rate probe (roofline denominator): 16 independent FFMA chains per thread
+__global__ void __launch_bounds__(256) k_fma_peak(float *out, int iters, float a, float b) {
+  float x[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) x[k] = (float)(threadIdx.x + k);
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) x[k] = fmaf(x[k], a, b);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) s += x[k];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
 // user rays (3 floats each) -> ray queue

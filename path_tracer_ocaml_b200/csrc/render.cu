@@ -321,7 +321,7 @@ static int render_impl(ptb_scene *s, const ptb_params &p, R *d_sums, cudaStream_
   const int shade_grid = d->sm_count * 4;
   for (long long first = 0; first < total; first += (long long)NB) {
     const unsigned n = (unsigned)std::min<long long>((long long)NB, total - first);
-    k_batch_ctl<<<1, 128, 0, st>>>(d->ctl, n);
+    k_batch_ctl<<<1, 128, 0, st>>>(d->ctl, n, p.max_bounces);
     const int pass0 = (int)(first / d->npix), i0 = (int)(first % d->npix);
     const int rg_grid = (int)std::min<long long>(((long long)n + 255) / 256, (long long)d->sm_count * 8);
     k_raygen<R><<<rg_grid, 256, 0, st>>>(rcst, d->pixel_list, pass0, i0, n, w.rays, nullptr, nullptr);
@@ -350,7 +350,7 @@ static int render_impl(ptb_scene *s, const ptb_params &p, R *d_sums, cudaStream_
       }
     }
   }
-  k_batch_ctl<<<1, 128, 0, st>>>(d->ctl, 0u);
+  k_batch_ctl<<<1, 128, 0, st>>>(d->ctl, 0u, p.max_bounces);
   ++launches;
   CK(cudaEventRecord(e1, st));
   CK(cudaGetLastError());
@@ -593,6 +593,39 @@ int ptb_intersect_batch(ptb_scene *s, const float *o, const float *dd, float t_m
     stats->ms_total = std::chrono::duration<double, std::milli>(clk::now() - t0).count();
   }
   return rc;
+}
+
+// FP32 issue-rate micro-benchmark: 16 independent FFMA chains per thread, enough resident warps to
+// saturate every SM sub-partition.  Returns 1e12 FFMA lane-operations per second (1 FFMA = 1 lane-op).
+int ptb_fp32_peak(int32_t device, double *tera_lane_ops, double *ms_out) {
+  if (!tera_lane_ops) return fail(PTB_E_INVALID, "fp32_peak: null argument");
+  int rc = check_device(device);
+  if (rc) return rc;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 14;
+  float *d_out = nullptr;
+  CK(cudaMalloc((void **)&d_out, (size_t)blocks * threads * sizeof(float)));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  double best = 1e30;
+  for (int rep = 0; rep < 5; ++rep) {
+    CK(cudaEventRecord(e0));
+    k_fma_peak<<<blocks, threads>>>(d_out, iters, 1.0001f, 0.9999f);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0) best = std::min(best, (double)ms);
+  }
+  CK(cudaGetLastError());
+  cudaFree(d_out);
+  cudaEventDestroy(e0), cudaEventDestroy(e1);
+  const double ops = (double)blocks * threads * (double)iters * 16.0;
+  *tera_lane_ops = ops / (best * 1e-3) / 1e12;
+  if (ms_out) *ms_out = best;
+  return PTB_OK;
 }
 
 int ptb_r2_stream(int32_t max_bounces, const int32_t *offsets, int64_t n, double *out, int32_t device) {
