@@ -131,6 +131,10 @@ int ptb_scene_set_background(ptb_scene *, int32_t kind, const double c0[3], cons
  * uploads it to `device`.  Returns build+upload milliseconds through *ms if non-NULL. */
 int ptb_scene_commit(ptb_scene *, int32_t device, double *ms);
 int64_t ptb_scene_primitive_count(const ptb_scene *);
+/* Shape of the committed device tree (the reference prints depth and a leaf-length histogram,
+ * shirley_spheres/bin/main.ml:263-267): out = {wide nodes, depth, worst-case stack entries, spheres,
+ * triangles, leaves, max leaf size, 0}. */
+int ptb_scene_tree_stats(const ptb_scene *, int32_t out[8]);
 
 /* Integrator.render (integrator.ml:130-156) with HOST image: `image_rgb` is 3*W*H doubles laid out
  * (y*W + x)*3 + c, row 0 = top — the Bimage f64 rgb layout the reference allocates

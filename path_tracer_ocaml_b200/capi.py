@@ -56,6 +56,7 @@ SYMBOLS = {
     "ptb_scene_set_background": (C.c_int, [_vp, C.c_int32, _dp, _dp]),
     "ptb_scene_commit": (C.c_int, [_vp, C.c_int32, _dp]),
     "ptb_scene_primitive_count": (C.c_int64, [_vp]),
+    "ptb_scene_tree_stats": (C.c_int, [_vp, _ip]),
     "ptb_render": (C.c_int, [_vp, _P(Params), _dp, _P(Stats)]),
     "ptb_render_device": (C.c_int, [_vp, _P(Params), _vp, _vp, _P(Stats)]),
     "ptb_resolve_device": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp]),

@@ -229,7 +229,21 @@ void build_wide_bvh(const HostScene &s, WideBVH *out) {
     }
   }
   out->depth = max_depth;
-  out->max_stack = 3 * max_depth + 2;
+  // exact worst case of the traversal stack: at a node with m children we push at most m-1 entries and
+  // descend into one child, whose subtree then needs its own worst case on top (children have larger
+  // indices than their parent, so one reverse sweep suffices)
+  std::vector<int> need(out->nodes.size(), 0);
+  for (int i = (int)out->nodes.size() - 1; i >= 0; --i) {
+    int m = 0, deepest = 0;
+    for (int k = 0; k < 4; ++k) {
+      int c = out->nodes[i].child[k];
+      if (c == EMPTY_CHILD) continue;
+      ++m;
+      if (c >= 0) deepest = std::max(deepest, need[c]);
+    }
+    need[i] = std::max(m - 1, 0) + deepest;
+  }
+  out->max_stack = need.empty() ? 1 : std::max(need[0], 1);
 }
 
 }  // namespace ptb

@@ -53,6 +53,7 @@ struct DScene {
   const Vec4<R> *tris;     // 3 per slot: (v0,_), (e1,_), (e2,_)
   const int32_t *sphere_id, *tri_id;    // slot -> caller index
   const int32_t *sphere_mat, *tri_mat;  // slot -> material row
+  const uint8_t *prim_kind;             // slot -> material kind, spheres then triangles, padded to 16 B
   const R *tri_uv;                      // 6 per slot
   const DMat *mats;
   const DTex<R> *texs;
@@ -66,14 +67,22 @@ struct DScene {
 // Wavefront queue entry = three Vec4 (48 B in float):
 //   ray queue : A = (origin, pixel)      B = (direction, R2 offset)   C = (attenuation, -)
 //   hit queue : A = (hit point, pixel)   B = (direction, R2 offset)   C = (attenuation, prim)
+// All queues are SEGMENTED: slot = segment * SEG + i, segment s holds seg_count[s] <= SEG valid entries.
+// A producer warp owns one open segment per output queue and touches the queue's global segment
+// counter once per SEG entries (instead of one contended return-value atomic per warp flush); a
+// consumer claims whole segments.  Only the last segment a warp opened can be partially filled.
+constexpr int SEG = 128;
 template <class R>
 struct Queue {
   Vec4<R> *A, *B, *C;
+  int32_t *seg_count;
 };
 
 struct Ctl {
-  unsigned int n_rays[MAX_BOUNCES + 1];            // rays entering bounce b of the current batch
-  unsigned int n_mat[MAX_BOUNCES][4];              // hits per material kind at bounce b
+  unsigned int nseg_rays[MAX_BOUNCES + 1];         // segments of the ray queue entering bounce b
+  unsigned int nseg_mat[MAX_BOUNCES][4];           // segments of the per-material hit queues at bounce b
+  unsigned int n_rays[MAX_BOUNCES + 1];            // rays traced at bounce b of the current batch
+  unsigned int cursor[MAX_BOUNCES + 1];            // segment-claim cursor per launch ([MAX_BOUNCES] = ad-hoc)
   unsigned long long rays_by_bounce[MAX_BOUNCES];  // accumulated over batches
   unsigned long long total_rays;
 };

@@ -183,10 +183,95 @@ __device__ __forceinline__ void tri_test(Vec4<R> v0, Vec4<R> e1v, Vec4<R> e2v, V
 }
 
 // ---------------------------------------------------------------------------------------------
-// BVH4 traversal.  `SMEM`: nodes/spheres/tris pointers address shared memory.
-// Stack entries live in shared memory as stack[level * blockDim + tid]: bank = tid % 32 for every
-// level, so pushes and pops never conflict whatever the per-lane depth.
+// memory access helpers: explicit ld.shared / st.shared (32-bit shared addresses) so the hot loop
+// never issues a generic load, and __ldg for the scenes that do not fit shared memory
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ Vec4<float> lds_vec4(unsigned addr, float) {
+  Vec4<float> v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ Vec4<double> lds_vec4(unsigned addr, double) {
+  Vec4<double> v;
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.z), "=d"(v.w) : "r"(addr + 16u));
+  return v;
+}
+__device__ __forceinline__ int4 lds_int4(unsigned addr) {
+  int4 v;
+  asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ int lds_i32(unsigned addr) {
+  int v;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ int lds_u8(unsigned addr) {
+  unsigned v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+  return (int)v;
+}
+__device__ __forceinline__ void sts_i32(unsigned addr, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(addr), "r"(v)); }
+__device__ __forceinline__ float lds_r(unsigned addr, float) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ double lds_r(unsigned addr, double) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_r(unsigned addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v)); }
+__device__ __forceinline__ void sts_r(unsigned addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v)); }
+__device__ __forceinline__ Vec4<float> ldg_vec4(const Vec4<float> *p) {
+  float4 v = __ldg(reinterpret_cast<const float4 *>(p));
+  return {v.x, v.y, v.z, v.w};
+}
+__device__ __forceinline__ Vec4<double> ldg_vec4(const Vec4<double> *p) {
+  double2 a = __ldg(reinterpret_cast<const double2 *>(p)), b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
+  return {a.x, a.y, b.x, b.y};
+}
+
+// where the scene lives for this launch: shared memory (staged by the block) or global memory
+template <class R, bool SMEM>
+struct SceneRef {
+  unsigned s_nodes, s_spheres, s_tris, s_kinds;  // shared-window byte addresses (SMEM)
+  const char *g_nodes;
+  const Vec4<R> *g_spheres, *g_tris;
+  const uint8_t *g_kinds;
+  // material kind of a primitive; `best` = slot | type << 30; table = spheres then triangles
+  __device__ __forceinline__ int kind(int best, int n_spheres) const {
+    const int idx = (best & 0x3FFFFFFF) + (((best >> 30) & 1) ? n_spheres : 0);
+    if (SMEM) return lds_u8(s_kinds + (unsigned)idx);
+    return (int)__ldg(g_kinds + idx);
+  }
+  __device__ __forceinline__ Vec4<R> nvec(int node, int k) const {
+    if (SMEM) return lds_vec4(s_nodes + (unsigned)node * (unsigned)sizeof(Node4<R>) + (unsigned)k * (unsigned)sizeof(Vec4<R>), R());
+    return ldg_vec4(reinterpret_cast<const Vec4<R> *>(g_nodes + (size_t)node * sizeof(Node4<R>)) + k);
+  }
+  __device__ __forceinline__ int4 children(int node) const {
+    if (SMEM) return lds_int4(s_nodes + (unsigned)node * (unsigned)sizeof(Node4<R>) + 6u * (unsigned)sizeof(Vec4<R>));
+    return __ldg(reinterpret_cast<const int4 *>(g_nodes + (size_t)node * sizeof(Node4<R>) + 6 * sizeof(Vec4<R>)));
+  }
+  __device__ __forceinline__ Vec4<R> sphere(int i) const {
+    if (SMEM) return lds_vec4(s_spheres + (unsigned)i * (unsigned)sizeof(Vec4<R>), R());
+    return ldg_vec4(g_spheres + i);
+  }
+  __device__ __forceinline__ Vec4<R> tri(int i, int k) const {
+    if (SMEM) return lds_vec4(s_tris + (unsigned)(3 * i + k) * (unsigned)sizeof(Vec4<R>), R());
+    return ldg_vec4(g_tris + 3 * (size_t)i + k);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// BVH4 traversal state of one lane.  The per-thread stack lives in shared memory as
+// stack[level][thread]: bank = thread % 32 at every level, so pushes and pops never conflict
+// whatever the per-lane depth.
+// ---------------------------------------------------------------------------------------------
+constexpr int TRAV_POP = INT32_MIN;  // `cur` sentinel: take the next stack entry
+
 #define PTB_CSWAP(ta, ca, tb, cb)   \
   {                                 \
     bool sw_ = tb < ta;             \
@@ -199,87 +284,102 @@ __device__ __forceinline__ void tri_test(Vec4<R> v0, Vec4<R> e1v, Vec4<R> e2v, V
   }
 
 template <class R>
-__device__ __forceinline__ void traverse(const char *__restrict__ nodes, const Vec4<R> *__restrict__ spheres,
-                                         const Vec4<R> *__restrict__ tris, V3<R> o, V3<R> d, R tmin, R &tbest,
-                                         int &best, int *stk_ref, R *stk_t, int stk_stride, int stk_cap) {
-  const R INF = Lim<R>::inf();
+struct Lane {
+  V3<R> o, d, idir, oid;
+  R a, inv_a, tmin, tbest;
+  int best, sp, cur;
+};
+
+template <class R>
+__device__ __forceinline__ void lane_init(Lane<R> &L, V3<R> o, V3<R> d, R tmin, R tmax) {
   auto safe_rcp = [](R x) {
     return (r_abs(x) < Lim<R>::tiny()) ? r_copysign(R(1) / Lim<R>::tiny(), x) : R(1) / x;
   };
-  const V3<R> idir = {safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z)};
-  const V3<R> oid = {o.x * idir.x, o.y * idir.y, o.z * idir.z};
-  // near/far plane arrays by direction sign: Vec4 index inside the node (lo = 0..2, hi = 3..5)
-  const int nx = d.x >= R(0) ? 0 : 3, ny = d.y >= R(0) ? 1 : 4, nz = d.z >= R(0) ? 2 : 5;
-  const int fx = 3 - nx, fy = 5 - ny, fz = 7 - nz;
-  const R a = dot(d, d);
-  const R inv_a = R(1) / a;
-  int sp = 0;
-  int cur = 0;
-  for (;;) {
-    if (cur >= 0) {
-      const Vec4<R> *n = reinterpret_cast<const Vec4<R> *>(nodes + (size_t)cur * sizeof(Node4<R>));
-      const Vec4<R> bnx = n[nx], bny = n[ny], bnz = n[nz], bfx = n[fx], bfy = n[fy], bfz = n[fz];
-      const int4 ch = *reinterpret_cast<const int4 *>(n + 6);
-      const R fs = Lim<R>::far_scale();
-#define PTB_SLAB(k)                                                                                  \
-  R tn##k = r_max(r_max(r_fma(bnx.k, idir.x, -oid.x), r_fma(bny.k, idir.y, -oid.y)),                 \
-                  r_max(r_fma(bnz.k, idir.z, -oid.z), tmin));                                        \
-  R tf##k = r_min(r_min(r_fma(bfx.k, idir.x, -oid.x), r_fma(bfy.k, idir.y, -oid.y)),                 \
-                  r_min(r_fma(bfz.k, idir.z, -oid.z), tbest)) * fs;                                  \
+  L.o = o, L.d = d;
+  L.idir = {safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z)};
+  L.oid = {o.x * L.idir.x, o.y * L.idir.y, o.z * L.idir.z};
+  L.a = dot(d, d);
+  L.inv_a = R(1) / L.a;
+  L.tmin = tmin, L.tbest = tmax;
+  L.best = -1, L.sp = 0, L.cur = 0;
+}
+
+// One traversal iteration: (inner node step) then (leaf step) then (pop).  Each part is optional per
+// lane; doing all three in one iteration keeps lanes of a warp in step.  Returns false when the ray
+// is finished.
+template <class R, bool SMEM>
+__device__ __forceinline__ bool lane_step(Lane<R> &L, const SceneRef<R, SMEM> &S, unsigned stk_ref, unsigned stk_t,
+                                          unsigned ref_stride, unsigned t_stride, int stk_cap) {
+  const R INF = Lim<R>::inf();
+  if (L.cur >= 0) {
+    const int nx = L.d.x >= R(0) ? 0 : 3, ny = L.d.y >= R(0) ? 1 : 4, nz = L.d.z >= R(0) ? 2 : 5;
+    const Vec4<R> bnx = S.nvec(L.cur, nx), bny = S.nvec(L.cur, ny), bnz = S.nvec(L.cur, nz);
+    const Vec4<R> bfx = S.nvec(L.cur, 3 - nx), bfy = S.nvec(L.cur, 5 - ny), bfz = S.nvec(L.cur, 7 - nz);
+    const int4 ch = S.children(L.cur);
+    const R fs = Lim<R>::far_scale();
+#define PTB_SLAB(k)                                                                                       \
+  R tn##k = r_max(r_max(r_fma(bnx.k, L.idir.x, -L.oid.x), r_fma(bny.k, L.idir.y, -L.oid.y)),              \
+                  r_max(r_fma(bnz.k, L.idir.z, -L.oid.z), L.tmin));                                       \
+  R tf##k = r_min(r_min(r_fma(bfx.k, L.idir.x, -L.oid.x), r_fma(bfy.k, L.idir.y, -L.oid.y)),              \
+                  r_min(r_fma(bfz.k, L.idir.z, -L.oid.z), L.tbest)) * fs;                                 \
   tn##k = (tn##k <= tf##k) ? tn##k : INF;
-      PTB_SLAB(x)
-      PTB_SLAB(y)
-      PTB_SLAB(z)
-      PTB_SLAB(w)
+    PTB_SLAB(x)
+    PTB_SLAB(y)
+    PTB_SLAB(z)
+    PTB_SLAB(w)
 #undef PTB_SLAB
-      int c0 = ch.x, c1 = ch.y, c2 = ch.z, c3 = ch.w;
-      R t0 = tnx, t1 = tny, t2 = tnz, t3 = tnw;
-      PTB_CSWAP(t0, c0, t1, c1)
-      PTB_CSWAP(t2, c2, t3, c3)
-      PTB_CSWAP(t0, c0, t2, c2)
-      PTB_CSWAP(t1, c1, t3, c3)
-      PTB_CSWAP(t1, c1, t2, c2)
-      if (t0 < INF) {
-        cur = c0;
-        if (t3 < INF && sp < stk_cap) {
-          stk_ref[sp * stk_stride] = c3;
-          stk_t[sp * stk_stride] = t3;
-          ++sp;
-        }
-        if (t2 < INF && sp < stk_cap) {
-          stk_ref[sp * stk_stride] = c2;
-          stk_t[sp * stk_stride] = t2;
-          ++sp;
-        }
-        if (t1 < INF && sp < stk_cap) {
-          stk_ref[sp * stk_stride] = c1;
-          stk_t[sp * stk_stride] = t1;
-          ++sp;
-        }
-        continue;
+    int c0 = ch.x, c1 = ch.y, c2 = ch.z, c3 = ch.w;
+    R t0 = tnx, t1 = tny, t2 = tnz, t3 = tnw;
+    PTB_CSWAP(t0, c0, t1, c1)
+    PTB_CSWAP(t2, c2, t3, c3)
+    PTB_CSWAP(t0, c0, t2, c2)
+    PTB_CSWAP(t1, c1, t3, c3)
+    PTB_CSWAP(t1, c1, t2, c2)
+    if (t0 < INF) {
+      L.cur = c0;
+      if (t3 < INF && L.sp < stk_cap) {
+        sts_i32(stk_ref + L.sp * ref_stride, c3);
+        sts_r(stk_t + L.sp * t_stride, t3);
+        ++L.sp;
+      }
+      if (t2 < INF && L.sp < stk_cap) {
+        sts_i32(stk_ref + L.sp * ref_stride, c2);
+        sts_r(stk_t + L.sp * t_stride, t2);
+        ++L.sp;
+      }
+      if (t1 < INF && L.sp < stk_cap) {
+        sts_i32(stk_ref + L.sp * ref_stride, c1);
+        sts_r(stk_t + L.sp * t_stride, t1);
+        ++L.sp;
       }
     } else {
-      const unsigned code = ~(unsigned)cur;
-      const int first = (int)(code & 0x3FFFFFFu);
-      const int cnt = (int)((code >> 26) & 15u) + 1;
-      if (((code >> 30) & 1u) == 0u) {
-        for (int i = 0; i < cnt; ++i)
-          sphere_test<R>(spheres[first + i], o, d, a, inv_a, tmin, tbest, best, first + i);
-      } else {
-        for (int i = 0; i < cnt; ++i) {
-          const Vec4<R> *t = tris + 3 * (size_t)(first + i);
-          tri_test<R>(t[0], t[1], t[2], o, d, tmin, tbest, best, (first + i) | (1 << 30));
-        }
-      }
-    }
-    // pop, skipping subtrees that start beyond the current best hit
-    for (;;) {
-      if (sp == 0) return;
-      --sp;
-      cur = stk_ref[sp * stk_stride];
-      if (stk_t[sp * stk_stride] <= tbest) break;
+      L.cur = TRAV_POP;
     }
   }
+  if (L.cur < 0 && L.cur != TRAV_POP) {
+    const unsigned code = ~(unsigned)L.cur;
+    const int first = (int)(code & 0x3FFFFFFu);
+    const int cnt = (int)((code >> 26) & 15u) + 1;
+    if (((code >> 30) & 1u) == 0u) {
+      for (int i = 0; i < cnt; ++i)
+        sphere_test<R>(S.sphere(first + i), L.o, L.d, L.a, L.inv_a, L.tmin, L.tbest, L.best, first + i);
+    } else {
+      for (int i = 0; i < cnt; ++i)
+        tri_test<R>(S.tri(first + i, 0), S.tri(first + i, 1), S.tri(first + i, 2), L.o, L.d, L.tmin, L.tbest, L.best,
+                    (first + i) | (1 << 30));
+    }
+    L.cur = TRAV_POP;
+  }
+  if (L.cur == TRAV_POP) {
+    // pop, skipping subtrees that start beyond the current best hit
+    for (;;) {
+      if (L.sp == 0) return false;
+      --L.sp;
+      L.cur = lds_i32(stk_ref + L.sp * ref_stride);
+      if (lds_r(stk_t + L.sp * t_stride, R()) <= L.tbest) break;
+    }
+  }
+  return true;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -302,6 +402,39 @@ __device__ __forceinline__ V3<R> background(const DScene<R> &sc, V3<R> d) {
   R t = R(0.5) * (dn.y + R(1));
   R s = R(1) - t;
   return {sc.bg0[0] * s + sc.bg1[0] * t, sc.bg0[1] * s + sc.bg1[1] * t, sc.bg0[2] * s + sc.bg1[2] * t};
+}
+
+// ---------------------------------------------------------------------------------------------
+// segmented-queue append (whole warp, convergent).  Lanes with `want` get a destination slot.
+// seg_base/seg_fill are warp-uniform: the warp's open segment in this queue (seg_base = NO_SEG: none).
+// ---------------------------------------------------------------------------------------------
+constexpr unsigned NO_SEG = 0xffffffffu;
+__device__ __forceinline__ unsigned seg_append(bool want, unsigned &seg_base, unsigned &seg_fill,
+                                               unsigned *__restrict__ nseg, int32_t *__restrict__ seg_count,
+                                               unsigned lane, unsigned lt_mask) {
+  const unsigned mask = __ballot_sync(0xffffffffu, want);
+  if (mask == 0u) return 0u;
+  const unsigned cnt = (unsigned)__popc(mask), rank = (unsigned)__popc(mask & lt_mask);
+  const unsigned room = (seg_base == NO_SEG) ? 0u : (unsigned)SEG - seg_fill;
+  if (cnt <= room) {
+    const unsigned dst = seg_base + seg_fill + rank;
+    seg_fill += cnt;
+    return dst;
+  }
+  unsigned s = 0;
+  if (lane == 0) {
+    s = atomicAdd(nseg, 1u);
+    if (seg_base != NO_SEG) seg_count[seg_base / SEG] = SEG;  // the old segment is (or becomes) full
+  }
+  s = __shfl_sync(0xffffffffu, s, 0);
+  const unsigned dst = rank < room ? seg_base + seg_fill + rank : s * SEG + (rank - room);
+  seg_base = s * SEG;
+  seg_fill = cnt - room;
+  return dst;
+}
+__device__ __forceinline__ void seg_close(unsigned seg_base, unsigned seg_fill, int32_t *__restrict__ seg_count,
+                                          unsigned lane) {
+  if (seg_base != NO_SEG && lane == 0) seg_count[seg_base / SEG] = (int32_t)seg_fill;
 }
 
 // =================================================================================================
@@ -332,104 +465,167 @@ __global__ void __launch_bounds__(256) k_raygen(RenderConst rc, const int32_t *_
     out.A[k] = {R(0), R(0), R(0), i2r(pixel, R())};
     out.B[k] = {dir.x, dir.y, dir.z, i2r(offset, R())};
     out.C[k] = {R(1), R(1), R(1), R(0)};
+    if (k % SEG == 0) out.seg_count[k / SEG] = (int32_t)(n - k < (unsigned)SEG ? n - k : (unsigned)SEG);  // dense
   }
 }
 
-// Stage 2+3 — traversal and primitive tests.
-// MODE 0: pipeline (miss -> background into sums; hit -> per-material queue)
-// MODE 1: intersect only (t and caller primitive index per ray)
-template <class R, int MODE>
-__global__ void __launch_bounds__(256)
-    k_trace(DScene<R> sc, Queue<R> rays, const unsigned *__restrict__ n_ptr, unsigned n_imm, Queue<R> q0,
-            Queue<R> q1, Queue<R> q2, unsigned *__restrict__ n_mat, int enqueue_hits, R *__restrict__ sums,
+// Stage 2+3 — traversal and primitive tests.  Persistent warps: every warp keeps its 32 lanes busy by
+// fetching new rays from the queue (chunked global cursor) whenever fewer than REFILL_BELOW lanes
+// are still traversing; finished lanes park their result in registers until that refill point, where
+// the whole warp runs the epilogue convergently:
+//   miss -> background * attenuation added into the per-pixel sums (integrator.ml:36)
+//   hit  -> appended to the queue of its material kind, warp-aggregated with __ballot_sync/__popc
+// MODE 0: pipeline.  MODE 1: intersect only (t and caller primitive index per ray).
+template <class R, int MODE, bool SMEM>
+__global__ void __launch_bounds__(SMEM ? 1024 : 256, 1)
+    k_trace(DScene<R> sc, Queue<R> rays, const unsigned *__restrict__ nseg_ptr, unsigned nseg_imm,
+            unsigned *__restrict__ cursor, int refill_below, Queue<R> q0, Queue<R> q1, Queue<R> q2,
+            unsigned *__restrict__ nseg_mat, unsigned *__restrict__ n_traced, int enqueue_hits, R *__restrict__ sums,
             R tmin_arg, R tmax_arg, R *__restrict__ out_t, int32_t *__restrict__ out_prim) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const unsigned n = n_ptr ? *n_ptr : n_imm;
+  const unsigned nseg = nseg_ptr ? *nseg_ptr : nseg_imm;  // segments in the input ray queue
   const int tid = threadIdx.x;
-  const char *nodes = reinterpret_cast<const char *>(sc.nodes);
-  const Vec4<R> *spheres = sc.spheres;
-  const Vec4<R> *tris = sc.tris;
-  size_t scene_bytes = 0;
-  if (sc.scene_in_smem) {
-    const size_t nb = (size_t)sc.n_nodes * sizeof(Node4<R>);
-    const size_t sb = (size_t)sc.n_spheres * sizeof(Vec4<R>);
-    const size_t tb = (size_t)sc.n_tris * 3 * sizeof(Vec4<R>);
-    scene_bytes = nb + sb + tb;
-    if (blockIdx.x * blockDim.x < n) {  // blocks without work skip the staging copy
-      int4 *dst = reinterpret_cast<int4 *>(smem);
-      const int4 *s0 = reinterpret_cast<const int4 *>(sc.nodes);
-      const int4 *s1 = reinterpret_cast<const int4 *>(sc.spheres);
-      const int4 *s2 = reinterpret_cast<const int4 *>(sc.tris);
-      for (size_t i = tid; i < nb / 16; i += blockDim.x) dst[i] = s0[i];
-      for (size_t i = tid; i < sb / 16; i += blockDim.x) dst[nb / 16 + i] = s1[i];
-      for (size_t i = tid; i < tb / 16; i += blockDim.x) dst[(nb + sb) / 16 + i] = s2[i];
-    }
-    nodes = reinterpret_cast<const char *>(smem);
-    spheres = reinterpret_cast<const Vec4<R> *>(smem + nb);
-    tris = reinterpret_cast<const Vec4<R> *>(smem + nb + sb);
+  const unsigned lane = tid & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const unsigned smem_base = (unsigned)__cvta_generic_to_shared(smem);
+  SceneRef<R, SMEM> S;
+  S.g_nodes = reinterpret_cast<const char *>(sc.nodes), S.g_spheres = sc.spheres, S.g_tris = sc.tris;
+  S.g_kinds = sc.prim_kind;
+  unsigned scene_bytes = 0;
+  if (SMEM) {
+    const unsigned nb = (unsigned)sc.n_nodes * (unsigned)sizeof(Node4<R>);
+    const unsigned sb = (unsigned)sc.n_spheres * (unsigned)sizeof(Vec4<R>);
+    const unsigned tb = (unsigned)sc.n_tris * 3u * (unsigned)sizeof(Vec4<R>);
+    const unsigned kb = ((unsigned)(sc.n_spheres + sc.n_tris) + 15u) & ~15u;  // prim_kind is padded to 16 B
+    scene_bytes = nb + sb + tb + kb;
+    int4 *dst = reinterpret_cast<int4 *>(smem);
+    const int4 *s0 = reinterpret_cast<const int4 *>(sc.nodes);
+    const int4 *s1 = reinterpret_cast<const int4 *>(sc.spheres);
+    const int4 *s2 = reinterpret_cast<const int4 *>(sc.tris);
+    const int4 *s3 = reinterpret_cast<const int4 *>(sc.prim_kind);
+    for (unsigned i = tid; i < nb / 16; i += blockDim.x) dst[i] = s0[i];
+    for (unsigned i = tid; i < sb / 16; i += blockDim.x) dst[nb / 16 + i] = s1[i];
+    for (unsigned i = tid; i < tb / 16; i += blockDim.x) dst[(nb + sb) / 16 + i] = s2[i];
+    for (unsigned i = tid; i < kb / 16; i += blockDim.x) dst[(nb + sb + tb) / 16 + i] = s3[i];
+    S.s_nodes = smem_base, S.s_spheres = smem_base + nb, S.s_tris = smem_base + nb + sb;
+    S.s_kinds = smem_base + nb + sb + tb;
     __syncthreads();
   }
-  int *stk_ref = reinterpret_cast<int *>(smem + scene_bytes) + tid;
-  R *stk_t = reinterpret_cast<R *>(smem + scene_bytes + (size_t)sc.stack_cap * blockDim.x * sizeof(int)) + tid;
-  const unsigned lane = tid & 31;
+  const unsigned ref_stride = blockDim.x * 4u, t_stride = blockDim.x * (unsigned)sizeof(R);
+  const unsigned stk_ref = smem_base + scene_bytes + (unsigned)tid * 4u;
+  const unsigned stk_t = smem_base + scene_bytes + (unsigned)sc.stack_cap * ref_stride + (unsigned)tid * (unsigned)sizeof(R);
 
-  for (unsigned base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
-    const unsigned i = base + tid;
-    const bool valid = i < n;
-    Vec4<R> A = {R(0), R(0), R(0), R(0)}, B = {R(0), R(0), R(1), R(0)};
-    if (valid) {
-      A = rays.A[i];
-      B = rays.B[i];
-    }
-    const V3<R> o = {A.x, A.y, A.z}, d = {B.x, B.y, B.z};
-    R tbest = (MODE == 0) ? Lim<R>::tmax() : tmax_arg;
-    const R tmin = (MODE == 0) ? R(0) : tmin_arg;
-    int best = -1;
-    if (valid) traverse<R>(nodes, spheres, tris, o, d, tmin, tbest, best, stk_ref, stk_t, blockDim.x, sc.stack_cap);
+  Lane<R> L;
+  L.cur = TRAV_POP, L.sp = 0, L.best = -1, L.tbest = R(0);
+  L.o = L.d = {R(0), R(0), R(1)};
+  bool has_ray = false;  // this lane is traversing
+  bool done = false;     // this lane holds a finished ray whose result is not flushed yet
+  unsigned ray_i = 0;
+  R a_w = R(0), b_w = R(0);           // the two integer payload words of the ray (pixel, offset)
+  V3<R> attn = {R(0), R(0), R(0)};    // the ray's attenuation (queue word C), carried in registers
+  unsigned chunk_next = 0, chunk_end = 0;  // warp-uniform: the claimed input segment [next, end)
+  bool more = true;                        // warp-uniform: the queue may still hold segments
+  unsigned fetched = 0;                    // warp-uniform: rays this warp has traced (statistics)
+  // warp-uniform: this warp's open segment in each material queue
+  unsigned sb0 = NO_SEG, sf0 = 0, sb1 = NO_SEG, sf1 = 0, sb2 = NO_SEG, sf2 = 0;
 
-    if (MODE == 1) {
-      if (valid) {
-        int slot = best & 0x3FFFFFFF;
-        int prim = best < 0 ? -1 : ((best >> 30) & 1 ? sc.n_spheres + sc.tri_id[slot] : sc.sphere_id[slot]);
-        out_t[i] = best < 0 ? R(NAN) : tbest;
-        out_prim[i] = prim;
+  for (;;) {
+    // ---------------- flush finished lanes (whole warp, convergent; no global loads) ------------
+    if (__ballot_sync(0xffffffffu, done)) {
+      if (MODE == 1) {
+        if (done) {
+          const int slot = L.best & 0x3FFFFFFF;
+          out_t[ray_i] = L.best < 0 ? R(NAN) : L.tbest;
+          out_prim[ray_i] = L.best < 0 ? -1 : ((L.best >> 30) & 1 ? sc.n_spheres + sc.tri_id[slot] : sc.sphere_id[slot]);
+        }
+      } else {
+        int kind = -1;
+        if (done) {
+          if (L.best < 0) {
+            // integrator.ml:36: emit0 + attn0 * background ray (emit0 == 0: Material.emit is black)
+            const V3<R> bg = background(sc, L.d);
+            const int pixel = r2i(a_w);
+            atomicAdd(&sums[3 * (size_t)pixel + 0], attn.x * bg.x);
+            atomicAdd(&sums[3 * (size_t)pixel + 1], attn.y * bg.y);
+            atomicAdd(&sums[3 * (size_t)pixel + 2], attn.z * bg.z);
+          } else if (enqueue_hits) {
+            kind = S.kind(L.best, sc.n_spheres);
+          }
+        }
+        // per-material segmented queues: no global atomic unless a segment fills up
+        const unsigned d0 = seg_append(kind == 0, sb0, sf0, &nseg_mat[0], q0.seg_count, lane, lt_mask);
+        const unsigned d1 = seg_append(kind == 1, sb1, sf1, &nseg_mat[1], q1.seg_count, lane, lt_mask);
+        const unsigned d2 = seg_append(kind == 2, sb2, sf2, &nseg_mat[2], q2.seg_count, lane, lt_mask);
+        if (kind >= 0) {
+          const unsigned dst = kind == 0 ? d0 : (kind == 1 ? d1 : d2);
+          const Queue<R> &q = (kind == 0) ? q0 : (kind == 1 ? q1 : q2);
+          q.A[dst] = {r_fma(L.tbest, L.d.x, L.o.x), r_fma(L.tbest, L.d.y, L.o.y), r_fma(L.tbest, L.d.z, L.o.z), a_w};
+          q.B[dst] = {L.d.x, L.d.y, L.d.z, b_w};
+          q.C[dst] = {attn.x, attn.y, attn.z, i2r(L.best, R())};
+        }
       }
+      done = false;
+    }
+    // ---------------- refill idle lanes from the queue (one parallel round trip) ----------------
+    unsigned idle = __ballot_sync(0xffffffffu, !has_ray);
+    if (more && idle) {
+      if (chunk_next >= chunk_end) {  // claim the next input segment
+        unsigned s = 0, c = 0;
+        if (lane == 0) {
+          s = atomicAdd(cursor, 1u);
+          if (s < nseg) c = (unsigned)rays.seg_count[s];
+        }
+        s = __shfl_sync(0xffffffffu, s, 0);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        chunk_next = s * SEG;
+        chunk_end = chunk_next + c;
+        if (s >= nseg) {
+          more = false;
+          chunk_next = chunk_end = 0;
+        }
+      }
+      if (more) {
+        const unsigned want = (unsigned)__popc(idle);
+        const unsigned avail = chunk_end - chunk_next;
+        const unsigned take = want < avail ? want : avail;
+        const unsigned rank = (unsigned)__popc(idle & lt_mask);
+        if (!has_ray && rank < take) {
+          ray_i = chunk_next + rank;
+          const Vec4<R> A = rays.A[ray_i], B = rays.B[ray_i];
+          if (MODE == 0) {
+            const Vec4<R> C = rays.C[ray_i];
+            attn = {C.x, C.y, C.z};
+          }
+          a_w = A.w, b_w = B.w;
+          lane_init<R>(L, V3<R>{A.x, A.y, A.z}, V3<R>{B.x, B.y, B.z}, (MODE == 0) ? R(0) : tmin_arg,
+                       (MODE == 0) ? Lim<R>::tmax() : tmax_arg);
+          has_ray = true;
+        }
+        chunk_next += take;
+        fetched += take;
+      }
+    }
+    const unsigned active = __ballot_sync(0xffffffffu, has_ray);
+    if (active == 0u) {
+      if (!more) break;
       continue;
     }
-    // ---- pipeline epilogue -------------------------------------------------------------------
-    int kind = -1;  // material kind of the hit, -1 = miss / nothing to enqueue
-    if (valid) {
-      if (best < 0) {
-        // integrator.ml:36: emit0 + attn0 * background ray  (emit0 == 0: Material.emit is black)
-        const Vec4<R> C = rays.C[i];
-        const V3<R> bg = background(sc, d);
-        const int pixel = r2i(A.w);
-        atomicAdd(&sums[3 * (size_t)pixel + 0], C.x * bg.x);
-        atomicAdd(&sums[3 * (size_t)pixel + 1], C.y * bg.y);
-        atomicAdd(&sums[3 * (size_t)pixel + 2], C.z * bg.z);
-      } else if (enqueue_hits) {
-        const int slot = best & 0x3FFFFFFF;
-        const int m = (best >> 30) & 1 ? sc.tri_mat[slot] : sc.sphere_mat[slot];
-        kind = sc.mats[m].kind;
+    // ---------------- traverse until too few lanes are left -------------------------------------
+    const int keep = more ? refill_below : 1;
+    do {
+      if (has_ray) {
+        if (!lane_step<R, SMEM>(L, S, stk_ref, stk_t, ref_stride, t_stride, sc.stack_cap)) {
+          has_ray = false;
+          done = true;
+        }
       }
-    }
-    // per-material queues, warp-aggregated append
-#pragma unroll
-    for (int m = 0; m < NUM_MAT_KINDS; ++m) {
-      const unsigned mask = __ballot_sync(0xffffffffu, kind == m);
-      if (mask == 0u) continue;
-      unsigned slot0 = 0;
-      if (lane == (unsigned)(__ffs(mask) - 1)) slot0 = atomicAdd(&n_mat[m], (unsigned)__popc(mask));
-      slot0 = __shfl_sync(0xffffffffu, slot0, __ffs(mask) - 1);
-      if (kind == m) {
-        const unsigned dst = slot0 + (unsigned)__popc(mask & ((1u << lane) - 1u));
-        const Queue<R> &q = (m == 0) ? q0 : (m == 1 ? q1 : q2);
-        const Vec4<R> C = rays.C[i];
-        q.A[dst] = {r_fma(tbest, d.x, o.x), r_fma(tbest, d.y, o.y), r_fma(tbest, d.z, o.z), A.w};
-        q.B[dst] = B;
-        q.C[dst] = {C.x, C.y, C.z, i2r(best, R())};
-      }
-    }
+    } while (__popc(__ballot_sync(0xffffffffu, has_ray)) >= keep);
+  }
+  if (MODE == 0) {
+    seg_close(sb0, sf0, q0.seg_count, lane);
+    seg_close(sb1, sf1, q1.seg_count, lane);
+    seg_close(sb2, sf2, q2.seg_count, lane);
+    if (lane == 0 && fetched) atomicAdd(n_traced, fetched);
   }
 }
 
@@ -438,22 +634,26 @@ __global__ void __launch_bounds__(256)
 template <class R>
 __global__ void __launch_bounds__(256)
     k_shade(DScene<R> sc, RenderConst rc, int bounce, Queue<R> q0, Queue<R> q1, Queue<R> q2,
-            const unsigned *__restrict__ n_mat, Queue<R> out, unsigned *__restrict__ n_out) {
+            const unsigned *__restrict__ nseg_mat, Queue<R> out, unsigned *__restrict__ nseg_out) {
   const unsigned lane = threadIdx.x & 31;
-  const unsigned n0 = n_mat[0], n1 = n_mat[1], n2 = n_mat[2];
-  const unsigned c0 = (n0 + 31) >> 5, c1 = (n1 + 31) >> 5, c2 = (n2 + 31) >> 5;
-  const unsigned total = c0 + c1 + c2;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const unsigned c0 = nseg_mat[0], c1 = nseg_mat[1], c2 = nseg_mat[2];
+  const unsigned total = c0 + c1 + c2;  // work item = one segment of one material's queue
   const unsigned warps = (gridDim.x * blockDim.x) >> 5;
   const int j = 2 + 2 * bounce;  // take_2d cursor (integrator.ml:20-28): every hit so far took two
   const double alpha_u = rc.alpha[j], alpha_v = rc.alpha[j + 1];
+  unsigned ob = NO_SEG, of = 0;  // warp-uniform: this warp's open segment in the output ray queue
   for (unsigned w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total; w += warps) {
     int m;
-    unsigned i, nm;
-    if (w < c0) m = 0, i = w * 32 + lane, nm = n0;
-    else if (w < c0 + c1) m = 1, i = (w - c0) * 32 + lane, nm = n1;
-    else m = 2, i = (w - c0 - c1) * 32 + lane, nm = n2;
+    unsigned seg;
+    if (w < c0) m = 0, seg = w;
+    else if (w < c0 + c1) m = 1, seg = w - c0;
+    else m = 2, seg = w - c0 - c1;
     const Queue<R> &q = (m == 0) ? q0 : (m == 1 ? q1 : q2);
-    const bool valid = i < nm;
+    const unsigned nm = (unsigned)q.seg_count[seg];
+   for (unsigned i0 = 0; i0 < nm; i0 += 32) {
+    const unsigned i = seg * SEG + i0 + lane;
+    const bool valid = i0 + lane < nm;
     bool alive = false;
     V3<R> no = {R(0), R(0), R(0)}, nd = {R(0), R(0), R(1)}, nattn = {R(0), R(0), R(0)};
     Vec4<R> A = {R(0), R(0), R(0), R(0)}, B = A;
@@ -558,24 +758,19 @@ __global__ void __launch_bounds__(256)
       nd = quat_transform(frame_inv, dir_ss);
       no = {r_fma(nd.x, R(1e-3), p.x), r_fma(nd.y, R(1e-3), p.y), r_fma(nd.z, R(1e-3), p.z)};
     }
-    const unsigned mask = __ballot_sync(0xffffffffu, alive);
-    if (mask) {
-      unsigned slot0 = 0;
-      const int leader = __ffs(mask) - 1;
-      if ((int)lane == leader) slot0 = atomicAdd(n_out, (unsigned)__popc(mask));
-      slot0 = __shfl_sync(0xffffffffu, slot0, leader);
-      if (alive) {
-        const unsigned dst = slot0 + (unsigned)__popc(mask & ((1u << lane) - 1u));
-        out.A[dst] = {no.x, no.y, no.z, A.w};
-        out.B[dst] = {nd.x, nd.y, nd.z, B.w};
-        out.C[dst] = {nattn.x, nattn.y, nattn.z, R(0)};
-      }
+    const unsigned dst = seg_append(alive, ob, of, nseg_out, out.seg_count, lane, lt_mask);
+    if (alive) {
+      out.A[dst] = {no.x, no.y, no.z, A.w};
+      out.B[dst] = {nd.x, nd.y, nd.z, B.w};
+      out.C[dst] = {nattn.x, nattn.y, nattn.z, R(0)};
     }
+   }
   }
+  seg_close(ob, of, out.seg_count, lane);
 }
 
 // batch bookkeeping: fold the finished batch's ray counts into the totals, reset the counters and
-// publish the next batch's size.
+// publish the next batch's ray-queue segment count.
 __global__ void k_batch_ctl(Ctl *ctl, unsigned next_n, int max_bounces) {
   const int t = threadIdx.x;
   if (t < max_bounces) {  // only bounces that were actually traced (integrator.ml:31-32)
@@ -584,9 +779,13 @@ __global__ void k_batch_ctl(Ctl *ctl, unsigned next_n, int max_bounces) {
     if (v) atomicAdd(&ctl->total_rays, (unsigned long long)v);
   }
   __syncthreads();
-  if (t <= MAX_BOUNCES) ctl->n_rays[t] = (t == 0) ? next_n : 0u;
+  if (t <= MAX_BOUNCES) {
+    ctl->n_rays[t] = 0u;
+    ctl->cursor[t] = 0u;
+    ctl->nseg_rays[t] = (t == 0) ? (next_n + SEG - 1) / SEG : 0u;
+  }
   if (t < MAX_BOUNCES) {
-    ctl->n_mat[t][0] = ctl->n_mat[t][1] = ctl->n_mat[t][2] = ctl->n_mat[t][3] = 0u;
+    ctl->nseg_mat[t][0] = ctl->nseg_mat[t][1] = ctl->nseg_mat[t][2] = ctl->nseg_mat[t][3] = 0u;
   }
 }
 
@@ -651,6 +850,7 @@ __global__ void k_pack_rays(const float *__restrict__ o, const float *__restrict
   if (i >= n) return;
   q.A[i] = {R(o[3 * i]), R(o[3 * i + 1]), R(o[3 * i + 2]), R(0)};
   q.B[i] = {R(d[3 * i]), R(d[3 * i + 1]), R(d[3 * i + 2]), R(0)};
+  if (i % SEG == 0) q.seg_count[i / SEG] = (int32_t)(n - i < SEG ? n - i : SEG);  // dense
 }
 
 }  // namespace ptb

@@ -28,11 +28,14 @@ struct Tables {
   DTex<R> *texs = nullptr;
   bool ready = false;
 };
+// producer warps that may each leave one partially filled segment behind in a queue (upper bound over
+// every launch shape used here), i.e. the slack a segmented queue needs on top of its dense capacity
+constexpr size_t MAX_PRODUCER_WARPS = 16384;
 template <class R>
 struct Work {
-  Queue<R> rays{nullptr, nullptr, nullptr};
+  Queue<R> rays{nullptr, nullptr, nullptr, nullptr};
   Queue<R> mq[NUM_MAT_KINDS]{};
-  size_t cap = 0;
+  size_t cap = 0;  // rays per batch the queues were sized for
 };
 
 struct DeviceState {
@@ -41,6 +44,7 @@ struct DeviceState {
   size_t smem_optin = 0;
   int32_t *sphere_id = nullptr, *tri_id = nullptr, *sphere_mat = nullptr, *tri_mat = nullptr;
   DMat *mats = nullptr;
+  uint8_t *prim_kind = nullptr;
   Tables<float> tf;
   Tables<double> td;
   Work<float> wf;
@@ -70,8 +74,8 @@ static void free_tables(Tables<R> &t) {
 }
 template <class R>
 static void free_queue(Queue<R> &q) {
-  cudaFree(q.A), cudaFree(q.B), cudaFree(q.C);
-  q = Queue<R>{nullptr, nullptr, nullptr};
+  cudaFree(q.A), cudaFree(q.B), cudaFree(q.C), cudaFree(q.seg_count);
+  q = Queue<R>{nullptr, nullptr, nullptr, nullptr};
 }
 template <class R>
 static void free_work(Work<R> &w) {
@@ -83,7 +87,7 @@ void destroy_device_state(DeviceState *d) {
   if (!d) return;
   if (d->device >= 0) cudaSetDevice(d->device);
   cudaFree(d->sphere_id), cudaFree(d->tri_id), cudaFree(d->sphere_mat), cudaFree(d->tri_mat);
-  cudaFree(d->mats), cudaFree(d->ctl), cudaFree(d->pixel_list);
+  cudaFree(d->mats), cudaFree(d->ctl), cudaFree(d->pixel_list), cudaFree(d->prim_kind);
   free_tables(d->tf), free_tables(d->td);
   free_work(d->wf), free_work(d->wd);
   delete d;
@@ -185,10 +189,12 @@ static int ensure_work(DeviceState *d, size_t cap) {
   Work<R> &w = d->work<R>();
   if (w.cap >= cap) return PTB_OK;
   free_work(w);
+  const size_t segs = (cap + SEG - 1) / SEG + MAX_PRODUCER_WARPS, slots = segs * SEG;
   auto alloc_q = [&](Queue<R> &q) -> int {
-    CK(cudaMalloc((void **)&q.A, cap * sizeof(Vec4<R>)));
-    CK(cudaMalloc((void **)&q.B, cap * sizeof(Vec4<R>)));
-    CK(cudaMalloc((void **)&q.C, cap * sizeof(Vec4<R>)));
+    CK(cudaMalloc((void **)&q.A, slots * sizeof(Vec4<R>)));
+    CK(cudaMalloc((void **)&q.B, slots * sizeof(Vec4<R>)));
+    CK(cudaMalloc((void **)&q.C, slots * sizeof(Vec4<R>)));
+    CK(cudaMalloc((void **)&q.seg_count, segs * sizeof(int32_t)));
     return PTB_OK;
   };
   int rc;
@@ -247,13 +253,14 @@ static DScene<R> make_dscene(ptb_scene *s, size_t *scene_bytes_out) {
   sc.nodes = t.nodes, sc.spheres = t.spheres, sc.tris = t.tris;
   sc.sphere_id = d->sphere_id, sc.tri_id = d->tri_id, sc.sphere_mat = d->sphere_mat, sc.tri_mat = d->tri_mat;
   sc.tri_uv = t.tri_uv, sc.mats = d->mats, sc.texs = t.texs;
+  sc.prim_kind = d->prim_kind;
   sc.n_nodes = (int)s->bvh.nodes.size();
   sc.n_spheres = (int)s->bvh.sphere_order.size();
   sc.n_tris = (int)s->bvh.tri_order.size();
   size_t bytes = (size_t)sc.n_nodes * sizeof(Node4<R>) + (size_t)sc.n_spheres * sizeof(Vec4<R>) +
-                 (size_t)sc.n_tris * 3 * sizeof(Vec4<R>);
+                 (size_t)sc.n_tris * 3 * sizeof(Vec4<R>) + (((size_t)sc.n_spheres + sc.n_tris + 15) / 16) * 16;
   sc.scene_in_smem = bytes <= 100 * 1024 ? 1 : 0;
-  sc.stack_cap = std::min(std::max(s->bvh.max_stack, 8), 96);
+  sc.stack_cap = std::min(std::max(s->bvh.max_stack, 4), 96);
   sc.bg_kind = s->host.bg_kind;
   for (int i = 0; i < 3; ++i) sc.bg0[i] = (R)s->host.bg0[i], sc.bg1[i] = (R)s->host.bg1[i];
   *scene_bytes_out = sc.scene_in_smem ? bytes : 0;
@@ -263,22 +270,57 @@ static DScene<R> make_dscene(ptb_scene *s, size_t *scene_bytes_out) {
 struct TraceLaunch {
   int block = 256, grid = 0;
   size_t smem = 0;
+  bool scene_smem = false;
 };
+// Launch shape of the traversal kernel.  Scene in shared memory: ONE block per SM, as many warps as the
+// per-thread stacks leave room for (up to 32), so the scene is staged once per SM.  Otherwise 256-thread
+// blocks at whatever occupancy the stack allows.
 template <class R, int MODE>
 static int trace_config(DeviceState *d, const DScene<R> &sc, size_t scene_bytes, TraceLaunch *tl) {
-  tl->block = 256;
-  for (;;) {
-    tl->smem = scene_bytes + (size_t)sc.stack_cap * tl->block * (sizeof(int) + sizeof(R));
-    if (tl->smem <= d->smem_optin || tl->block == 64) break;
-    tl->block /= 2;
+  const size_t per_thread = (size_t)sc.stack_cap * (sizeof(int) + sizeof(R));
+  tl->scene_smem = sc.scene_in_smem != 0;
+  if (tl->scene_smem) {
+    tl->block = 1024;
+    while (tl->block > 128 && scene_bytes + per_thread * tl->block > d->smem_optin) tl->block -= 128;
+    tl->smem = scene_bytes + per_thread * tl->block;
+    if (tl->smem > d->smem_optin) return fail(PTB_E_NOMEM, "trace: scene + stack do not fit shared memory");
+    CK(cudaFuncSetAttribute(k_trace<R, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl->smem));
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<R, MODE, true>, tl->block, tl->smem));
+    if (per_sm < 1) return fail(PTB_E_CUDA, "trace: kernel cannot be resident");
+    tl->grid = d->sm_count * per_sm;
+  } else {
+    tl->block = 256;
+    while (tl->block > 64 && per_thread * tl->block > d->smem_optin / 2) tl->block /= 2;
+    tl->smem = per_thread * tl->block;
+    CK(cudaFuncSetAttribute(k_trace<R, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl->smem));
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<R, MODE, false>, tl->block, tl->smem));
+    if (per_sm < 1) return fail(PTB_E_CUDA, "trace: kernel cannot be resident");
+    tl->grid = d->sm_count * per_sm;
   }
-  if (tl->smem > d->smem_optin) return fail(PTB_E_NOMEM, "trace: scene + stack do not fit shared memory");
-  CK(cudaFuncSetAttribute(k_trace<R, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl->smem));
-  int per_sm = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<R, MODE>, tl->block, tl->smem));
-  if (per_sm < 1) return fail(PTB_E_CUDA, "trace: kernel cannot be resident");
-  tl->grid = d->sm_count * per_sm;
   return PTB_OK;
+}
+static int refill_below() {
+  static int v = -1;
+  if (v < 0) {
+    v = 14;
+    if (const char *e = std::getenv("PTB_REFILL")) v = std::min(32, std::max(1, std::atoi(e)));
+  }
+  return v;
+}
+template <class R, int MODE>
+static void launch_trace(const TraceLaunch &tl, cudaStream_t st, const DScene<R> &sc, Queue<R> rays,
+                         const unsigned *nseg_ptr, unsigned nseg_imm, unsigned *cursor, Queue<R> *mq, unsigned *nseg_mat,
+                         unsigned *n_traced, int enqueue_hits, R *sums, R tmin, R tmax, R *out_t, int32_t *out_prim) {
+  if (tl.scene_smem)
+    k_trace<R, MODE, true><<<tl.grid, tl.block, tl.smem, st>>>(sc, rays, nseg_ptr, nseg_imm, cursor, refill_below(), mq[0],
+                                                               mq[1], mq[2], nseg_mat, n_traced, enqueue_hits, sums, tmin,
+                                                               tmax, out_t, out_prim);
+  else
+    k_trace<R, MODE, false><<<tl.grid, tl.block, tl.smem, st>>>(sc, rays, nseg_ptr, nseg_imm, cursor, refill_below(), mq[0],
+                                                                mq[1], mq[2], nseg_mat, n_traced, enqueue_hits, sums, tmin,
+                                                                tmax, out_t, out_prim);
 }
 
 static size_t batch_capacity() {
@@ -336,16 +378,15 @@ static int render_impl(ptb_scene *s, const ptb_params &p, R *d_sums, cudaStream_
         tev.push_back(a);
         tev.push_back(z);
       }
-      k_trace<R, 0><<<tl.grid, tl.block, tl.smem, st>>>(sc, w.rays, &d->ctl->n_rays[b], 0u, w.mq[0], w.mq[1],
-                                                        w.mq[2], &d->ctl->n_mat[b][0], last ? 0 : 1, d_sums,
-                                                        R(0), R(0), nullptr, nullptr);
+      launch_trace<R, 0>(tl, st, sc, w.rays, &d->ctl->nseg_rays[b], 0u, &d->ctl->cursor[b], w.mq, &d->ctl->nseg_mat[b][0],
+                         &d->ctl->n_rays[b], last ? 0 : 1, d_sums, R(0), R(0), nullptr, nullptr);
       if (profile) CK(cudaEventRecord(tev.back(), st));
       ++launches;
       if (!last) {
         // a path that is still alive after the last allowed bounce contributes black
         // (integrator.ml:31-32), so the last bounce needs no scatter
-        k_shade<R><<<shade_grid, 256, 0, st>>>(sc, rcst, b, w.mq[0], w.mq[1], w.mq[2], &d->ctl->n_mat[b][0], w.rays,
-                                               &d->ctl->n_rays[b + 1]);
+        k_shade<R><<<shade_grid, 256, 0, st>>>(sc, rcst, b, w.mq[0], w.mq[1], w.mq[2], &d->ctl->nseg_mat[b][0], w.rays,
+                                               &d->ctl->nseg_rays[b + 1]);
         ++launches;
       }
     }
@@ -473,12 +514,34 @@ int ptb_scene_commit(ptb_scene *s, int32_t device, double *ms) {
   if ((rc = upload(&d->sphere_mat, smat))) return rc;
   if ((rc = upload(&d->tri_mat, tmat))) return rc;
   if ((rc = upload(&d->mats, mats))) return rc;
+  std::vector<uint8_t> kinds(((smat.size() + tmat.size() + 15) / 16) * 16 + 16, 0);
+  for (size_t k = 0; k < smat.size(); ++k) kinds[k] = (uint8_t)h.mat[smat[k]].kind;
+  for (size_t k = 0; k < tmat.size(); ++k) kinds[smat.size() + k] = (uint8_t)h.mat[tmat[k]].kind;
+  if ((rc = upload(&d->prim_kind, kinds))) return rc;
   CK(cudaMalloc((void **)&d->ctl, sizeof(Ctl)));
   CK(cudaMemset(d->ctl, 0, sizeof(Ctl)));
   s->committed = true;
   if ((rc = ensure_tables<float>(s))) return rc;
   CK(cudaDeviceSynchronize());
   if (ms) *ms = std::chrono::duration<double, std::milli>(clk::now() - t0).count();
+  return PTB_OK;
+}
+
+int ptb_scene_tree_stats(const ptb_scene *s, int32_t out[8]) {
+  if (!s || !out) return fail(PTB_E_INVALID, "tree_stats: null argument");
+  if (!s->committed) return fail(PTB_E_STATE, "scene is not committed (call ptb_scene_commit)");
+  std::memset(out, 0, 8 * sizeof(int32_t));
+  out[0] = (int32_t)s->bvh.nodes.size();
+  out[1] = s->bvh.depth;
+  out[2] = s->bvh.max_stack;
+  out[3] = (int32_t)s->bvh.sphere_order.size();
+  out[4] = (int32_t)s->bvh.tri_order.size();
+  int leaves = 0;
+  for (const WideNode &n : s->bvh.nodes)
+    for (int k = 0; k < 4; ++k)
+      if (n.child[k] < 0 && n.child[k] != EMPTY_CHILD) ++leaves;
+  out[5] = leaves;
+  out[6] = LEAF_MAX;
   return PTB_OK;
 }
 
@@ -539,9 +602,9 @@ int ptb_intersect_batch_device(ptb_scene *s, const float *d_o, const float *d_d,
   for (int64_t first = 0; first < n; first += (int64_t)cap) {
     const long long m = std::min<int64_t>((int64_t)cap, n - first);
     k_pack_rays<float><<<(unsigned)((m + 255) / 256), 256, 0, st>>>(d_o + 3 * first, d_d + 3 * first, m, w.rays);
-    k_trace<float, 1><<<tl.grid, tl.block, tl.smem, st>>>(sc, w.rays, nullptr, (unsigned)m, w.mq[0], w.mq[1], w.mq[2],
-                                                          nullptr, 0, nullptr, t_min, t_max, d_t + first,
-                                                          d_prim + first);
+    CK(cudaMemsetAsync(&d->ctl->cursor[MAX_BOUNCES], 0, sizeof(unsigned), st));
+    launch_trace<float, 1>(tl, st, sc, w.rays, nullptr, (unsigned)((m + SEG - 1) / SEG), &d->ctl->cursor[MAX_BOUNCES], w.mq,
+                           nullptr, nullptr, 0, nullptr, t_min, t_max, d_t + first, d_prim + first);
     launches += 2;
   }
   CK(cudaEventRecord(e1, st));
@@ -675,6 +738,7 @@ int ptb_raygen(const ptb_params *p, int64_t first, int64_t n, int32_t *pixel, in
   CK(cudaMalloc((void **)&q.A, nn * 16));
   CK(cudaMalloc((void **)&q.B, nn * 16));
   CK(cudaMalloc((void **)&q.C, nn * 16));
+  CK(cudaMalloc((void **)&q.seg_count, (nn / SEG + 1) * sizeof(int32_t)));
   CK(cudaMalloc((void **)&d_cx, nn * 8));
   CK(cudaMalloc((void **)&d_cy, nn * 8));
   if (n > 0) {
@@ -695,7 +759,7 @@ int ptb_raygen(const ptb_params *p, int64_t first, int64_t n, int32_t *pixel, in
     if (offset) offset[i] = oi;
     if (dir_xyz) dir_xyz[3 * i] = B[i].x, dir_xyz[3 * i + 1] = B[i].y, dir_xyz[3 * i + 2] = B[i].z;
   }
-  cudaFree(q.A), cudaFree(q.B), cudaFree(q.C), cudaFree(d_cx), cudaFree(d_cy), cudaFree(tmp.pixel_list);
+  cudaFree(q.A), cudaFree(q.B), cudaFree(q.C), cudaFree(q.seg_count), cudaFree(d_cx), cudaFree(d_cy), cudaFree(tmp.pixel_list);
   return PTB_OK;
 }
 
@@ -719,8 +783,9 @@ int ptb_first_hit(ptb_scene *s, const ptb_params *p, float *t_hit, int32_t *prim
   CK(cudaMalloc((void **)&d_t, n * 4));
   CK(cudaMalloc((void **)&d_p, n * 4));
   k_raygen<float><<<(unsigned)((n + 255) / 256), 256>>>(rcst, d->pixel_list, 0, 0, (unsigned)n, w.rays, nullptr, nullptr);
-  k_trace<float, 1><<<tl.grid, tl.block, tl.smem>>>(sc, w.rays, nullptr, (unsigned)n, w.mq[0], w.mq[1], w.mq[2], nullptr,
-                                                    0, nullptr, 0.0f, FLT_MAX, d_t, d_p);
+  CK(cudaMemsetAsync(&d->ctl->cursor[MAX_BOUNCES], 0, sizeof(unsigned), 0));
+  launch_trace<float, 1>(tl, 0, sc, w.rays, nullptr, (unsigned)((n + SEG - 1) / SEG), &d->ctl->cursor[MAX_BOUNCES], w.mq,
+                         nullptr, nullptr, 0, nullptr, 0.0f, FLT_MAX, d_t, d_p);
   CK(cudaGetLastError());
   std::vector<float> ht(n);
   std::vector<int32_t> hp(n);

@@ -81,6 +81,11 @@ class Scene:
         self.committed_on, self.commit_ms = device, ms.value
         return ms.value
 
+    def tree_stats(self):
+        out = np.zeros(8, dtype=np.int32)
+        check(lib().ptb_scene_tree_stats(self.h, iptr(out)))
+        return dict(zip(("nodes", "depth", "max_stack", "spheres", "triangles", "leaves", "leaf_max"), map(int, out)))
+
     # ---- read-back --------------------------------------------------------------------------------
     def tables(self):
         L = lib()

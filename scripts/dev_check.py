@@ -10,7 +10,7 @@ import pyoracle as O
 W, H, spp, mb = (int(v) for v in (sys.argv[1:5] if len(sys.argv) >= 5 else (600, 300, 32, 8)))
 scene = P.shirley_spheres(W, H)
 integ = P.Integrator(scene, W, H, spp, mb, device=0)
-print("commit ms", scene.commit_ms)
+print("commit ms", scene.commit_ms, scene.tree_stats())
 osc = O.OracleScene(scene.tables())
 t0 = time.time(); ref, cn = osc.render(integ.params, n_threads=os.cpu_count()); t_cpu = time.time() - t0
 print(f"oracle: {t_cpu:.2f}s  {cn.paths/t_cpu/1e6:.2f} Mpaths/s  rays {cn.rays}")
