@@ -298,7 +298,7 @@ def main():
         "dtype": "f32 (R2 sample stream and cx,cy in f64, bit-exact)", "data": "synthetic",
         "config": {"workload": WORKLOAD if spp == SPP else f"DEV OVERRIDE spp={spp}: " + WORKLOAD,
                    "sharding": f"reference tile list (Tile.split 1024 px), tile t -> rank t mod {world}",
-                   "l2": "no flush needed: each 4 Mi-path wavefront batch streams ~800 MB of queue state (> 126 MB L2)",
+                   "l2": "no flush needed: each 64 Mi-path wavefront batch streams ~12 GB of queue state (>> 126 MB L2)",
                    "paths_per_step": paths_per_step},
         "roofline": {"bound": "fp32_issue", "kernel": "k_trace<float,0>", "achieved": trace_tlops, "peak": peak.value,
                      "unit": "Tlane-op/s", "frac": trace_tlops / peak.value, "traffic": traffic,

@@ -26,6 +26,18 @@ namespace ptb {
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float r_sqrt(float x) { return sqrtf(x); }
 __device__ __forceinline__ double r_sqrt(double x) { return sqrt(x); }
+// float: hardware approximations (MUFU.RCP / MUFU.SQRT, <= 2 ulp) — well inside the float32 error of the
+// quantities they feed (t, 1/d); double: exact IEEE, the validation mode mirrors the reference
+__device__ __forceinline__ float r_rcp(float x) { return __fdividef(1.0f, x); }
+__device__ __forceinline__ double r_rcp(double x) { return 1.0 / x; }
+__device__ __forceinline__ float r_div(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ double r_div(double a, double b) { return a / b; }
+__device__ __forceinline__ float r_sqrt_fast(float x) {
+  float y;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ double r_sqrt_fast(double x) { return sqrt(x); }
 __device__ __forceinline__ float r_abs(float x) { return fabsf(x); }
 __device__ __forceinline__ double r_abs(double x) { return fabs(x); }
 __device__ __forceinline__ float r_min(float a, float b) { return fminf(a, b); }
@@ -151,9 +163,9 @@ __device__ __forceinline__ void sphere_test(Vec4<R> s, V3<R> o, V3<R> d, R a, R 
   V3<R> w = {r_fma(d.x, boa, -f.x), r_fma(d.y, boa, -f.y), r_fma(d.z, boa, -f.z)};
   R disc = r2 - dot(w, w);
   if (disc >= R(0)) {
-    R q = bp + r_copysign(r_sqrt(a * disc), bp);
+    R q = bp + r_copysign(r_sqrt_fast(a * disc), bp);
     R c = dot(f, f) - r2;
-    R t = (c > R(0)) ? c / q : q * inv_a;
+    R t = (c > R(0)) ? r_div(c, q) : q * inv_a;
     if (t >= tmin && t <= tbest) {  // `<=`: a later equal t wins (lib.rs:171-176, shape_tree.ml:303-309)
       tbest = t;
       best = id;
@@ -293,13 +305,13 @@ struct Lane {
 template <class R>
 __device__ __forceinline__ void lane_init(Lane<R> &L, V3<R> o, V3<R> d, R tmin, R tmax) {
   auto safe_rcp = [](R x) {
-    return (r_abs(x) < Lim<R>::tiny()) ? r_copysign(R(1) / Lim<R>::tiny(), x) : R(1) / x;
+    return (r_abs(x) < Lim<R>::tiny()) ? r_copysign(R(1) / Lim<R>::tiny(), x) : r_rcp(x);
   };
   L.o = o, L.d = d;
   L.idir = {safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z)};
   L.oid = {o.x * L.idir.x, o.y * L.idir.y, o.z * L.idir.z};
   L.a = dot(d, d);
-  L.inv_a = R(1) / L.a;
+  L.inv_a = r_rcp(L.a);
   L.tmin = tmin, L.tbest = tmax;
   L.best = -1, L.sp = 0, L.cur = 0;
 }
@@ -487,6 +499,12 @@ __global__ void __launch_bounds__(SMEM ? 1024 : 256, 1)
   const int tid = threadIdx.x;
   const unsigned lane = tid & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
+  // claim granularity: a quarter, half or whole segment, so that a small launch (late bounces) still
+  // spreads over every persistent warp and a big one pays one cursor atomic per 128 rays
+  const unsigned per_warp = nseg * (unsigned)SEG / (gridDim.x * (blockDim.x >> 5));
+  const unsigned claim_shift = per_warp >= 512u ? 0u : (per_warp >= 256u ? 1u : 2u);  // units per segment = 1 << shift
+  const unsigned claim = (unsigned)SEG >> claim_shift;
+  const unsigned nunits = nseg << claim_shift;
   const unsigned smem_base = (unsigned)__cvta_generic_to_shared(smem);
   SceneRef<R, SMEM> S;
   S.g_nodes = reinterpret_cast<const char *>(sc.nodes), S.g_spheres = sc.spheres, S.g_tris = sc.tris;
@@ -569,17 +587,19 @@ __global__ void __launch_bounds__(SMEM ? 1024 : 256, 1)
     // ---------------- refill idle lanes from the queue (one parallel round trip) ----------------
     unsigned idle = __ballot_sync(0xffffffffu, !has_ray);
     if (more && idle) {
-      if (chunk_next >= chunk_end) {  // claim the next input segment
-        unsigned s = 0, c = 0;
+      if (chunk_next >= chunk_end) {  // claim the next unit (segment or part of one) of the input queue
+        unsigned u = 0, c = 0;
         if (lane == 0) {
-          s = atomicAdd(cursor, 1u);
-          if (s < nseg) c = (unsigned)rays.seg_count[s];
+          u = atomicAdd(cursor, 1u);
+          if (u < nunits) c = (unsigned)rays.seg_count[u >> claim_shift];
         }
-        s = __shfl_sync(0xffffffffu, s, 0);
+        u = __shfl_sync(0xffffffffu, u, 0);
         c = __shfl_sync(0xffffffffu, c, 0);
-        chunk_next = s * SEG;
-        chunk_end = chunk_next + c;
-        if (s >= nseg) {
+        const unsigned off = (u & ((1u << claim_shift) - 1u)) * claim;  // offset of the unit inside its segment
+        const unsigned lim = c < off + claim ? c : off + claim;         // valid entries end here
+        chunk_next = (u >> claim_shift) * SEG + off;
+        chunk_end = lim > off ? (u >> claim_shift) * SEG + lim : chunk_next;
+        if (u >= nunits) {
           more = false;
           chunk_next = chunk_end = 0;
         }
@@ -638,20 +658,22 @@ __global__ void __launch_bounds__(256)
   const unsigned lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
   const unsigned c0 = nseg_mat[0], c1 = nseg_mat[1], c2 = nseg_mat[2];
-  const unsigned total = c0 + c1 + c2;  // work item = one segment of one material's queue
+  const unsigned total = (c0 + c1 + c2) * (SEG / 32);  // work item = 32 entries of one segment of one material
   const unsigned warps = (gridDim.x * blockDim.x) >> 5;
   const int j = 2 + 2 * bounce;  // take_2d cursor (integrator.ml:20-28): every hit so far took two
   const double alpha_u = rc.alpha[j], alpha_v = rc.alpha[j + 1];
   unsigned ob = NO_SEG, of = 0;  // warp-uniform: this warp's open segment in the output ray queue
   for (unsigned w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total; w += warps) {
     int m;
-    unsigned seg;
-    if (w < c0) m = 0, seg = w;
-    else if (w < c0 + c1) m = 1, seg = w - c0;
-    else m = 2, seg = w - c0 - c1;
+    unsigned seg = w / (SEG / 32);
+    const unsigned i0 = (w % (SEG / 32)) * 32;
+    if (seg < c0) m = 0;
+    else if (seg < c0 + c1) m = 1, seg -= c0;
+    else m = 2, seg -= c0 + c1;
     const Queue<R> &q = (m == 0) ? q0 : (m == 1 ? q1 : q2);
     const unsigned nm = (unsigned)q.seg_count[seg];
-   for (unsigned i0 = 0; i0 < nm; i0 += 32) {
+    if (i0 >= nm) continue;
+   {
     const unsigned i = seg * SEG + i0 + lane;
     const bool valid = i0 + lane < nm;
     bool alive = false;

@@ -38,6 +38,27 @@ struct Work {
   size_t cap = 0;  // rays per batch the queues were sized for
 };
 
+// Per-device work buffers (wavefront queues, control block, pixel list).  They belong to the device,
+// not to a scene: committing another scene must not reallocate gigabytes of queue memory.
+struct DevicePool {
+  Work<float> wf;
+  Work<double> wd;
+  Ctl *ctl = nullptr;
+  int32_t *pixel_list = nullptr;
+  std::vector<int32_t> pixel_list_host;
+  int pl_W = 0, pl_H = 0, pl_rank = -1, pl_world = 0, npix = 0;
+  template <class R>
+  Work<R> &work();
+};
+template <>
+Work<float> &DevicePool::work<float>() { return wf; }
+template <>
+Work<double> &DevicePool::work<double>() { return wd; }
+static DevicePool *pool_for(int device) {
+  static DevicePool pools[64];
+  return &pools[device & 63];
+}
+
 struct DeviceState {
   int device = -1;
   int sm_count = 0;
@@ -47,25 +68,14 @@ struct DeviceState {
   uint8_t *prim_kind = nullptr;
   Tables<float> tf;
   Tables<double> td;
-  Work<float> wf;
-  Work<double> wd;
-  Ctl *ctl = nullptr;
-  int32_t *pixel_list = nullptr;
-  std::vector<int32_t> pixel_list_host;
-  int pl_W = 0, pl_H = 0, pl_rank = -1, pl_world = 0, npix = 0;
+  DevicePool *pool = nullptr;
   template <class R>
   Tables<R> &tables();
-  template <class R>
-  Work<R> &work();
 };
 template <>
 Tables<float> &DeviceState::tables<float>() { return tf; }
 template <>
 Tables<double> &DeviceState::tables<double>() { return td; }
-template <>
-Work<float> &DeviceState::work<float>() { return wf; }
-template <>
-Work<double> &DeviceState::work<double>() { return wd; }
 
 template <class R>
 static void free_tables(Tables<R> &t) {
@@ -87,9 +97,8 @@ void destroy_device_state(DeviceState *d) {
   if (!d) return;
   if (d->device >= 0) cudaSetDevice(d->device);
   cudaFree(d->sphere_id), cudaFree(d->tri_id), cudaFree(d->sphere_mat), cudaFree(d->tri_mat);
-  cudaFree(d->mats), cudaFree(d->ctl), cudaFree(d->pixel_list), cudaFree(d->prim_kind);
+  cudaFree(d->mats), cudaFree(d->prim_kind);
   free_tables(d->tf), free_tables(d->td);
-  free_work(d->wf), free_work(d->wd);
   delete d;
 }
 
@@ -185,7 +194,7 @@ static int ensure_tables(ptb_scene *s) {
 }
 
 template <class R>
-static int ensure_work(DeviceState *d, size_t cap) {
+static int ensure_work(DevicePool *d, size_t cap) {
   Work<R> &w = d->work<R>();
   if (w.cap >= cap) return PTB_OK;
   free_work(w);
@@ -207,7 +216,7 @@ static int ensure_work(DeviceState *d, size_t cap) {
 
 // this rank's pixels, in the reference's tile order (Tile.split ~max_area:1024, integrator.ml:132-133;
 // tile t belongs to rank t mod world), row-major inside a tile like Tile.iter (tile.ml:71-79)
-static int ensure_pixel_list(DeviceState *d, int W, int H, int rank, int world) {
+static int ensure_pixel_list(DevicePool *d, int W, int H, int rank, int world) {
   if (d->pixel_list && d->pl_W == W && d->pl_H == H && d->pl_rank == rank && d->pl_world == world) return PTB_OK;
   std::vector<TileRect> tiles;
   tile_split(W, H, 32 * 32, &tiles);
@@ -324,7 +333,7 @@ static void launch_trace(const TraceLaunch &tl, cudaStream_t st, const DScene<R>
 }
 
 static size_t batch_capacity() {
-  size_t nb = (size_t)1 << 22;
+  size_t nb = (size_t)1 << 26;
   if (const char *e = std::getenv("PTB_BATCH")) {
     long long v = std::atoll(e);
     if (v >= 1024) nb = (size_t)v;
@@ -341,13 +350,15 @@ static int render_impl(ptb_scene *s, const ptb_params &p, R *d_sums, cudaStream_
   if ((rc = ensure_tables<R>(s))) return rc;
   int world = p.tile_world > 0 ? p.tile_world : 1;
   if (p.tile_rank < 0 || p.tile_rank >= world) return fail(PTB_E_INVALID, "render: tile_rank out of range");
-  if ((rc = ensure_pixel_list(d, p.width, p.height, p.tile_rank, world))) return rc;
+  DevicePool *pl = d->pool;
+  if ((rc = ensure_pixel_list(pl, p.width, p.height, p.tile_rank, world))) return rc;
   RenderConst rcst;
-  if ((rc = fill_render_const(p, d->npix, &rcst))) return rc;
-  const long long total = (long long)d->npix * p.samples_per_pixel;
+  if ((rc = fill_render_const(p, pl->npix, &rcst))) return rc;
+  const long long total = (long long)pl->npix * p.samples_per_pixel;
   const size_t NB = std::min<size_t>(batch_capacity(), (size_t)std::max<long long>(total, 1));
-  if ((rc = ensure_work<R>(d, NB))) return rc;
-  Work<R> &w = d->work<R>();
+  if ((rc = ensure_work<R>(pl, NB))) return rc;
+  Work<R> &w = pl->work<R>();
+  Ctl *ctl = pl->ctl;
   size_t scene_bytes = 0;
   DScene<R> sc = make_dscene<R>(s, &scene_bytes);
   TraceLaunch tl;
@@ -357,16 +368,16 @@ static int render_impl(ptb_scene *s, const ptb_params &p, R *d_sums, cudaStream_
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
-  CK(cudaMemsetAsync(d->ctl, 0, sizeof(Ctl), st));
+  CK(cudaMemsetAsync(ctl, 0, sizeof(Ctl), st));
   CK(cudaEventRecord(e0, st));
   uint64_t launches = 0;
   const int shade_grid = d->sm_count * 4;
   for (long long first = 0; first < total; first += (long long)NB) {
     const unsigned n = (unsigned)std::min<long long>((long long)NB, total - first);
-    k_batch_ctl<<<1, 128, 0, st>>>(d->ctl, n, p.max_bounces);
-    const int pass0 = (int)(first / d->npix), i0 = (int)(first % d->npix);
+    k_batch_ctl<<<1, 128, 0, st>>>(ctl, n, p.max_bounces);
+    const int pass0 = (int)(first / pl->npix), i0 = (int)(first % pl->npix);
     const int rg_grid = (int)std::min<long long>(((long long)n + 255) / 256, (long long)d->sm_count * 8);
-    k_raygen<R><<<rg_grid, 256, 0, st>>>(rcst, d->pixel_list, pass0, i0, n, w.rays, nullptr, nullptr);
+    k_raygen<R><<<rg_grid, 256, 0, st>>>(rcst, pl->pixel_list, pass0, i0, n, w.rays, nullptr, nullptr);
     launches += 2;
     for (int b = 0; b < p.max_bounces; ++b) {
       const bool last = (b == p.max_bounces - 1);
@@ -378,27 +389,27 @@ static int render_impl(ptb_scene *s, const ptb_params &p, R *d_sums, cudaStream_
         tev.push_back(a);
         tev.push_back(z);
       }
-      launch_trace<R, 0>(tl, st, sc, w.rays, &d->ctl->nseg_rays[b], 0u, &d->ctl->cursor[b], w.mq, &d->ctl->nseg_mat[b][0],
-                         &d->ctl->n_rays[b], last ? 0 : 1, d_sums, R(0), R(0), nullptr, nullptr);
+      launch_trace<R, 0>(tl, st, sc, w.rays, &ctl->nseg_rays[b], 0u, &ctl->cursor[b], w.mq, &ctl->nseg_mat[b][0],
+                         &ctl->n_rays[b], last ? 0 : 1, d_sums, R(0), R(0), nullptr, nullptr);
       if (profile) CK(cudaEventRecord(tev.back(), st));
       ++launches;
       if (!last) {
         // a path that is still alive after the last allowed bounce contributes black
         // (integrator.ml:31-32), so the last bounce needs no scatter
-        k_shade<R><<<shade_grid, 256, 0, st>>>(sc, rcst, b, w.mq[0], w.mq[1], w.mq[2], &d->ctl->nseg_mat[b][0], w.rays,
-                                               &d->ctl->nseg_rays[b + 1]);
+        k_shade<R><<<shade_grid, 256, 0, st>>>(sc, rcst, b, w.mq[0], w.mq[1], w.mq[2], &ctl->nseg_mat[b][0], w.rays,
+                                               &ctl->nseg_rays[b + 1]);
         ++launches;
       }
     }
   }
-  k_batch_ctl<<<1, 128, 0, st>>>(d->ctl, 0u, p.max_bounces);
+  k_batch_ctl<<<1, 128, 0, st>>>(ctl, 0u, p.max_bounces);
   ++launches;
   CK(cudaEventRecord(e1, st));
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(st));
   if (stats) {
     Ctl host;
-    CK(cudaMemcpy(&host, d->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&host, ctl, sizeof(Ctl), cudaMemcpyDeviceToHost));
     stats->paths = (uint64_t)total;
     stats->rays = host.total_rays;
     for (int b = 0; b < MAX_BOUNCES; ++b) stats->rays_by_bounce[b] = host.rays_by_bounce[b];
@@ -518,8 +529,11 @@ int ptb_scene_commit(ptb_scene *s, int32_t device, double *ms) {
   for (size_t k = 0; k < smat.size(); ++k) kinds[k] = (uint8_t)h.mat[smat[k]].kind;
   for (size_t k = 0; k < tmat.size(); ++k) kinds[smat.size() + k] = (uint8_t)h.mat[tmat[k]].kind;
   if ((rc = upload(&d->prim_kind, kinds))) return rc;
-  CK(cudaMalloc((void **)&d->ctl, sizeof(Ctl)));
-  CK(cudaMemset(d->ctl, 0, sizeof(Ctl)));
+  d->pool = pool_for(device);
+  if (!d->pool->ctl) {
+    CK(cudaMalloc((void **)&d->pool->ctl, sizeof(Ctl)));
+    CK(cudaMemset(d->pool->ctl, 0, sizeof(Ctl)));
+  }
   s->committed = true;
   if ((rc = ensure_tables<float>(s))) return rc;
   CK(cudaDeviceSynchronize());
@@ -586,10 +600,11 @@ int ptb_intersect_batch_device(ptb_scene *s, const float *d_o, const float *d_d,
   int rc = require_committed(s, device);
   if (rc) return rc;
   DeviceState *d = s->dev;
+  DevicePool *pl = d->pool;
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t cap = std::min<size_t>(batch_capacity() * 4, (size_t)std::max<int64_t>(n, 1));
-  if ((rc = ensure_work<float>(d, cap))) return rc;
-  Work<float> &w = d->work<float>();
+  const size_t cap = std::min<size_t>(batch_capacity(), (size_t)std::max<int64_t>(n, 1));
+  if ((rc = ensure_work<float>(pl, cap))) return rc;
+  Work<float> &w = pl->work<float>();
   size_t scene_bytes = 0;
   DScene<float> sc = make_dscene<float>(s, &scene_bytes);
   TraceLaunch tl;
@@ -602,8 +617,8 @@ int ptb_intersect_batch_device(ptb_scene *s, const float *d_o, const float *d_d,
   for (int64_t first = 0; first < n; first += (int64_t)cap) {
     const long long m = std::min<int64_t>((int64_t)cap, n - first);
     k_pack_rays<float><<<(unsigned)((m + 255) / 256), 256, 0, st>>>(d_o + 3 * first, d_d + 3 * first, m, w.rays);
-    CK(cudaMemsetAsync(&d->ctl->cursor[MAX_BOUNCES], 0, sizeof(unsigned), st));
-    launch_trace<float, 1>(tl, st, sc, w.rays, nullptr, (unsigned)((m + SEG - 1) / SEG), &d->ctl->cursor[MAX_BOUNCES], w.mq,
+    CK(cudaMemsetAsync(&pl->ctl->cursor[MAX_BOUNCES], 0, sizeof(unsigned), st));
+    launch_trace<float, 1>(tl, st, sc, w.rays, nullptr, (unsigned)((m + SEG - 1) / SEG), &pl->ctl->cursor[MAX_BOUNCES], w.mq,
                            nullptr, nullptr, 0, nullptr, t_min, t_max, d_t + first, d_prim + first);
     launches += 2;
   }
@@ -719,19 +734,13 @@ int ptb_raygen(const ptb_params *p, int64_t first, int64_t n, int32_t *pixel, in
   if (!p || n < 0 || first < 0) return fail(PTB_E_INVALID, "raygen: bad args");
   int rc = check_device(p->device);
   if (rc) return rc;
-  DeviceState tmp;  // scratch state: raygen needs no scene
+  DevicePool &tmp = *pool_for(p->device);  // raygen needs no scene
   int world = p->tile_world > 0 ? p->tile_world : 1;
   if ((rc = ensure_pixel_list(&tmp, p->width, p->height, p->tile_rank, world))) return rc;
   RenderConst rcst;
-  if ((rc = fill_render_const(*p, tmp.npix, &rcst))) {
-    cudaFree(tmp.pixel_list);
-    return rc;
-  }
+  if ((rc = fill_render_const(*p, tmp.npix, &rcst))) return rc;
   const long long total = (long long)tmp.npix * p->samples_per_pixel;
-  if (first + n > total) {
-    cudaFree(tmp.pixel_list);
-    return fail(PTB_E_INVALID, "raygen: sample range exceeds W*H*spp of this rank");
-  }
+  if (first + n > total) return fail(PTB_E_INVALID, "raygen: sample range exceeds W*H*spp of this rank");
   const size_t nn = (size_t)std::max<int64_t>(n, 1);
   Queue<float> q;
   double *d_cx = nullptr, *d_cy = nullptr;
@@ -759,7 +768,7 @@ int ptb_raygen(const ptb_params *p, int64_t first, int64_t n, int32_t *pixel, in
     if (offset) offset[i] = oi;
     if (dir_xyz) dir_xyz[3 * i] = B[i].x, dir_xyz[3 * i + 1] = B[i].y, dir_xyz[3 * i + 2] = B[i].z;
   }
-  cudaFree(q.A), cudaFree(q.B), cudaFree(q.C), cudaFree(q.seg_count), cudaFree(d_cx), cudaFree(d_cy), cudaFree(tmp.pixel_list);
+  cudaFree(q.A), cudaFree(q.B), cudaFree(q.C), cudaFree(q.seg_count), cudaFree(d_cx), cudaFree(d_cy);
   return PTB_OK;
 }
 
@@ -768,12 +777,13 @@ int ptb_first_hit(ptb_scene *s, const ptb_params *p, float *t_hit, int32_t *prim
   int rc = require_committed(s, p->device);
   if (rc) return rc;
   DeviceState *d = s->dev;
-  if ((rc = ensure_pixel_list(d, p->width, p->height, 0, 1))) return rc;
+  DevicePool *pl = d->pool;
+  if ((rc = ensure_pixel_list(pl, p->width, p->height, 0, 1))) return rc;
   RenderConst rcst;
-  if ((rc = fill_render_const(*p, d->npix, &rcst))) return rc;
-  const size_t n = (size_t)d->npix;
-  if ((rc = ensure_work<float>(d, n))) return rc;
-  Work<float> &w = d->work<float>();
+  if ((rc = fill_render_const(*p, pl->npix, &rcst))) return rc;
+  const size_t n = (size_t)pl->npix;
+  if ((rc = ensure_work<float>(pl, n))) return rc;
+  Work<float> &w = pl->work<float>();
   size_t scene_bytes = 0;
   DScene<float> sc = make_dscene<float>(s, &scene_bytes);
   TraceLaunch tl;
@@ -782,9 +792,9 @@ int ptb_first_hit(ptb_scene *s, const ptb_params *p, float *t_hit, int32_t *prim
   int32_t *d_p = nullptr;
   CK(cudaMalloc((void **)&d_t, n * 4));
   CK(cudaMalloc((void **)&d_p, n * 4));
-  k_raygen<float><<<(unsigned)((n + 255) / 256), 256>>>(rcst, d->pixel_list, 0, 0, (unsigned)n, w.rays, nullptr, nullptr);
-  CK(cudaMemsetAsync(&d->ctl->cursor[MAX_BOUNCES], 0, sizeof(unsigned), 0));
-  launch_trace<float, 1>(tl, 0, sc, w.rays, nullptr, (unsigned)((n + SEG - 1) / SEG), &d->ctl->cursor[MAX_BOUNCES], w.mq,
+  k_raygen<float><<<(unsigned)((n + 255) / 256), 256>>>(rcst, pl->pixel_list, 0, 0, (unsigned)n, w.rays, nullptr, nullptr);
+  CK(cudaMemsetAsync(&pl->ctl->cursor[MAX_BOUNCES], 0, sizeof(unsigned), 0));
+  launch_trace<float, 1>(tl, 0, sc, w.rays, nullptr, (unsigned)((n + SEG - 1) / SEG), &pl->ctl->cursor[MAX_BOUNCES], w.mq,
                          nullptr, nullptr, 0, nullptr, 0.0f, FLT_MAX, d_t, d_p);
   CK(cudaGetLastError());
   std::vector<float> ht(n);
@@ -793,7 +803,7 @@ int ptb_first_hit(ptb_scene *s, const ptb_params *p, float *t_hit, int32_t *prim
   CK(cudaMemcpy(hp.data(), d_p, n * 4, cudaMemcpyDeviceToHost));
   cudaFree(d_t), cudaFree(d_p);
   for (size_t k = 0; k < n; ++k) {
-    int px = d->pixel_list_host[k];
+    int px = pl->pixel_list_host[k];
     t_hit[px] = ht[k];
     prim[px] = hp[k];
   }
