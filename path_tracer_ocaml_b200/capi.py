@@ -3,7 +3,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libptb200.so")
+# PTB_LIB: development aid for A/B timing of two builds of the SAME library (never a fallback)
+LIB_PATH = os.environ.get("PTB_LIB") or os.path.join(_HERE, "lib", "libptb200.so")
 
 PTB_TEX_SOLID, PTB_TEX_CHECKER = 0, 1
 PTB_MAT_LAMBERTIAN, PTB_MAT_METAL, PTB_MAT_DIELECTRIC = 0, 1, 2

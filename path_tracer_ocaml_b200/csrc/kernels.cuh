@@ -28,15 +28,20 @@ __device__ __forceinline__ float r_sqrt(float x) { return sqrtf(x); }
 __device__ __forceinline__ double r_sqrt(double x) { return sqrt(x); }
 // float: hardware approximations (MUFU.RCP / MUFU.SQRT, <= 2 ulp) — well inside the float32 error of the
 // quantities they feed (t, 1/d); double: exact IEEE, the validation mode mirrors the reference
-__device__ __forceinline__ float r_rcp(float x) { return __fdividef(1.0f, x); }
+__device__ __forceinline__ float r_rcp(float x) {  // one MUFU.RCP
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ double r_rcp(double x) { return 1.0 / x; }
 __device__ __forceinline__ float r_div(float a, float b) { return __fdividef(a, b); }
 __device__ __forceinline__ double r_div(double a, double b) { return a / b; }
-__device__ __forceinline__ float r_sqrt_fast(float x) {
+__device__ __forceinline__ float r_sqrt_fast(float x) {  // one MUFU.SQRT (no subnormal rescaling)
   float y;
-  asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+
 __device__ __forceinline__ double r_sqrt_fast(double x) { return sqrt(x); }
 __device__ __forceinline__ float r_abs(float x) { return fabsf(x); }
 __device__ __forceinline__ double r_abs(double x) { return fabs(x); }
@@ -153,11 +158,29 @@ __device__ __forceinline__ Quat<R> frame_from_normal(V3<R> n) {
 // ---------------------------------------------------------------------------------------------
 // Ray-sphere in the numerically robust form the reference uses (sphere.ml:35-54; lib.rs:130-166):
 // discriminant from the perpendicular offset, q = b' + sign(b')*sqrt(a*disc), t = c>0 ? c/q : q/a.
+// `s.w` holds r^2 here (SceneRef::sphere squares it or reads the pre-squared shared-memory copy).
+// float: straight-line.  A negative discriminant makes sqrt.approx return NaN, NaN propagates into t and
+// every comparison with NaN is false, so the miss needs no branch (the Rust kernel's NaN masking,
+// lib.rs:160-166, is the same idea).
+__device__ __forceinline__ void sphere_test(Vec4<float> s, V3<float> o, V3<float> d, float a, float inv_a,
+                                            float tmin, float &tbest, int &best, int id) {
+  const V3<float> f = {s.x - o.x, s.y - o.y, s.z - o.z};
+  const float bp = dot(f, d);
+  const float boa = bp * inv_a;
+  const V3<float> w = {fmaf(d.x, boa, -f.x), fmaf(d.y, boa, -f.y), fmaf(d.z, boa, -f.z)};
+  const float disc = fmaf(-w.x, w.x, fmaf(-w.y, w.y, fmaf(-w.z, w.z, s.w)));
+  const float q = bp + copysignf(r_sqrt_fast(a * disc), bp);
+  const float c = fmaf(f.x, f.x, fmaf(f.y, f.y, fmaf(f.z, f.z, -s.w)));
+  const float t = (c > 0.0f) ? c * r_rcp(q) : q * inv_a;
+  const bool ok = (t >= tmin) && (t <= tbest);  // `<=`: a later equal t wins (lib.rs:171-176)
+  tbest = ok ? t : tbest;
+  best = ok ? id : best;
+}
 template <class R>
 __device__ __forceinline__ void sphere_test(Vec4<R> s, V3<R> o, V3<R> d, R a, R inv_a, R tmin, R &tbest,
                                             int &best, int id) {
   V3<R> f = {s.x - o.x, s.y - o.y, s.z - o.z};
-  R r2 = s.w * s.w;
+  R r2 = s.w;
   R bp = dot(f, d);
   R boa = bp * inv_a;
   V3<R> w = {r_fma(d.x, boa, -f.x), r_fma(d.y, boa, -f.y), r_fma(d.z, boa, -f.z)};
@@ -209,6 +232,13 @@ __device__ __forceinline__ Vec4<double> lds_vec4(unsigned addr, double) {
   asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.z), "=d"(v.w) : "r"(addr + 16u));
   return v;
 }
+__device__ __forceinline__ void sts_vec4(unsigned addr, Vec4<float> v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
+}
+__device__ __forceinline__ void sts_vec4(unsigned addr, Vec4<double> v) {
+  asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(addr), "d"(v.x), "d"(v.y));
+  asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(addr + 16u), "d"(v.z), "d"(v.w));
+}
 __device__ __forceinline__ int4 lds_int4(unsigned addr) {
   int4 v;
   asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
@@ -237,6 +267,23 @@ __device__ __forceinline__ double lds_r(unsigned addr, double) {
 }
 __device__ __forceinline__ void sts_r(unsigned addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v)); }
 __device__ __forceinline__ void sts_r(unsigned addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v)); }
+// traversal-stack entry = (child ref, t_near): 8 B in float (one 64-bit shared access), 16 B in double
+__device__ __forceinline__ void stk_store(unsigned addr, int ref, float t) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(ref), "r"(__float_as_int(t)));
+}
+__device__ __forceinline__ void stk_store(unsigned addr, int ref, double t) {
+  asm volatile("st.shared.s32 [%0], %1;" ::"r"(addr), "r"(ref));
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr + 8u), "d"(t));
+}
+__device__ __forceinline__ void stk_load(unsigned addr, int &ref, float &t) {
+  int tb;
+  asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(ref), "=r"(tb) : "r"(addr));
+  t = __int_as_float(tb);
+}
+__device__ __forceinline__ void stk_load(unsigned addr, int &ref, double &t) {
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(ref) : "r"(addr));
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(t) : "r"(addr + 8u));
+}
 __device__ __forceinline__ Vec4<float> ldg_vec4(const Vec4<float> *p) {
   float4 v = __ldg(reinterpret_cast<const float4 *>(p));
   return {v.x, v.y, v.z, v.w};
@@ -253,23 +300,28 @@ struct SceneRef {
   const char *g_nodes;
   const Vec4<R> *g_spheres, *g_tris;
   const uint8_t *g_kinds;
+  static constexpr unsigned ROW = 4u * (unsigned)sizeof(R);  // one SoA row of a node: 4 children of one plane
   // material kind of a primitive; `best` = slot | type << 30; table = spheres then triangles
   __device__ __forceinline__ int kind(int best, int n_spheres) const {
     const int idx = (best & 0x3FFFFFFF) + (((best >> 30) & 1) ? n_spheres : 0);
     if (SMEM) return lds_u8(s_kinds + (unsigned)idx);
     return (int)__ldg(g_kinds + idx);
   }
-  __device__ __forceinline__ Vec4<R> nvec(int node, int k) const {
-    if (SMEM) return lds_vec4(s_nodes + (unsigned)node * (unsigned)sizeof(Node4<R>) + (unsigned)k * (unsigned)sizeof(Vec4<R>), R());
-    return ldg_vec4(reinterpret_cast<const Vec4<R> *>(g_nodes + (size_t)node * sizeof(Node4<R>)) + k);
+  // row at byte offset `off` of node `node`
+  __device__ __forceinline__ Vec4<R> nrow(int node, unsigned off) const {
+    if (SMEM) return lds_vec4(s_nodes + (unsigned)node * (unsigned)sizeof(Node4<R>) + off, R());
+    return ldg_vec4(reinterpret_cast<const Vec4<R> *>(g_nodes + (size_t)node * sizeof(Node4<R>) + off));
   }
   __device__ __forceinline__ int4 children(int node) const {
-    if (SMEM) return lds_int4(s_nodes + (unsigned)node * (unsigned)sizeof(Node4<R>) + 6u * (unsigned)sizeof(Vec4<R>));
-    return __ldg(reinterpret_cast<const int4 *>(g_nodes + (size_t)node * sizeof(Node4<R>) + 6 * sizeof(Vec4<R>)));
+    if (SMEM) return lds_int4(s_nodes + (unsigned)node * (unsigned)sizeof(Node4<R>) + 6u * ROW);
+    return __ldg(reinterpret_cast<const int4 *>(g_nodes + (size_t)node * sizeof(Node4<R>) + 6 * ROW));
   }
+  // (cx, cy, cz, r^2): the shared-memory copy is squared once when the block stages it
   __device__ __forceinline__ Vec4<R> sphere(int i) const {
     if (SMEM) return lds_vec4(s_spheres + (unsigned)i * (unsigned)sizeof(Vec4<R>), R());
-    return ldg_vec4(g_spheres + i);
+    Vec4<R> v = ldg_vec4(g_spheres + i);
+    v.w *= v.w;
+    return v;
   }
   __device__ __forceinline__ Vec4<R> tri(int i, int k) const {
     if (SMEM) return lds_vec4(s_tris + (unsigned)(3 * i + k) * (unsigned)sizeof(Vec4<R>), R());
@@ -279,10 +331,13 @@ struct SceneRef {
 
 // ---------------------------------------------------------------------------------------------
 // BVH4 traversal state of one lane.  The per-thread stack lives in shared memory as
-// stack[level][thread]: bank = thread % 32 at every level, so pushes and pops never conflict
-// whatever the per-lane depth.
+// stack[level][thread] with one (ref, t_near) entry per level: consecutive lanes are consecutive
+// entries at every level, so pushes and pops never bank-conflict whatever the per-lane depth.
+// Entry 0 of every thread is a permanent sentinel (TRAV_DONE, -inf) written at kernel start: the pop
+// loop needs no empty check, it simply pops the sentinel when the ray is finished.
 // ---------------------------------------------------------------------------------------------
-constexpr int TRAV_POP = INT32_MIN;  // `cur` sentinel: take the next stack entry
+constexpr int TRAV_POP = INT32_MIN;       // `cur` sentinel: take the next stack entry (== EMPTY_CHILD, never a ref)
+constexpr int TRAV_DONE = INT32_MIN + 1;  // the stack's bottom entry
 
 #define PTB_CSWAP(ta, ca, tb, cb)   \
   {                                 \
@@ -299,11 +354,14 @@ template <class R>
 struct Lane {
   V3<R> o, d, idir, oid;
   R a, inv_a, tmin, tbest;
-  int best, sp, cur;
+  int best, cur;
+  unsigned sp;             // shared-window byte address of the next free stack entry
+  unsigned onx, ony, onz;  // byte offsets of the near x / y / z plane rows inside a node (by direction sign)
 };
 
 template <class R>
-__device__ __forceinline__ void lane_init(Lane<R> &L, V3<R> o, V3<R> d, R tmin, R tmax) {
+__device__ __forceinline__ void lane_init(Lane<R> &L, V3<R> o, V3<R> d, R tmin, R tmax, unsigned sp0) {
+  constexpr unsigned ROW = 4u * (unsigned)sizeof(R);
   auto safe_rcp = [](R x) {
     return (r_abs(x) < Lim<R>::tiny()) ? r_copysign(R(1) / Lim<R>::tiny(), x) : r_rcp(x);
   };
@@ -313,27 +371,38 @@ __device__ __forceinline__ void lane_init(Lane<R> &L, V3<R> o, V3<R> d, R tmin, 
   L.a = dot(d, d);
   L.inv_a = r_rcp(L.a);
   L.tmin = tmin, L.tbest = tmax;
-  L.best = -1, L.sp = 0, L.cur = 0;
+  L.best = -1, L.cur = 0;
+  L.sp = sp0;
+  L.onx = d.x >= R(0) ? 0u : 3u * ROW;  // rows: lo.x lo.y lo.z hi.x hi.y hi.z
+  L.ony = d.y >= R(0) ? ROW : 4u * ROW;
+  L.onz = d.z >= R(0) ? 2u * ROW : 5u * ROW;
 }
 
 // One traversal iteration: (inner node step) then (leaf step) then (pop).  Each part is optional per
 // lane; doing all three in one iteration keeps lanes of a warp in step.  Returns false when the ray
-// is finished.
-template <class R, bool SMEM>
-__device__ __forceinline__ bool lane_step(Lane<R> &L, const SceneRef<R, SMEM> &S, unsigned stk_ref, unsigned stk_t,
-                                          unsigned ref_stride, unsigned t_stride, int stk_cap) {
+// is finished.  TMIN0: t_min is the constant 0 (render pipeline).  FULLSORT: hit children are pushed
+// strictly far-to-near (5-exchange network); otherwise only the nearest child is singled out (3
+// exchanges) and the others are pushed in slot order — every pushed child is still visited unless its
+// t_near exceeds the best hit, so the closest hit is unchanged.  CHECK: stack overflow guard (only when the
+// tree's worst case exceeds the capacity).
+template <class R, bool SMEM, bool TMIN0, bool FULLSORT, bool CHECK>
+__device__ __forceinline__ bool lane_step(Lane<R> &L, const SceneRef<R, SMEM> &S, unsigned stride, unsigned sp_limit) {
+  constexpr unsigned ROW = 4u * (unsigned)sizeof(R);
   const R INF = Lim<R>::inf();
   if (L.cur >= 0) {
-    const int nx = L.d.x >= R(0) ? 0 : 3, ny = L.d.y >= R(0) ? 1 : 4, nz = L.d.z >= R(0) ? 2 : 5;
-    const Vec4<R> bnx = S.nvec(L.cur, nx), bny = S.nvec(L.cur, ny), bnz = S.nvec(L.cur, nz);
-    const Vec4<R> bfx = S.nvec(L.cur, 3 - nx), bfy = S.nvec(L.cur, 5 - ny), bfz = S.nvec(L.cur, 7 - nz);
+    const Vec4<R> bnx = S.nrow(L.cur, L.onx), bny = S.nrow(L.cur, L.ony), bnz = S.nrow(L.cur, L.onz);
+    const Vec4<R> bfx = S.nrow(L.cur, 3u * ROW - L.onx), bfy = S.nrow(L.cur, 5u * ROW - L.ony),
+                  bfz = S.nrow(L.cur, 7u * ROW - L.onz);
     const int4 ch = S.children(L.cur);
-    const R fs = Lim<R>::far_scale();
+    const R tmin = TMIN0 ? R(0) : L.tmin;
+    // float boxes are padded outward on the host (render.cu box_lo/box_hi), which covers the rounding of
+    // the plane distances; the unpadded double boxes get a relative slack on the far side instead
 #define PTB_SLAB(k)                                                                                       \
   R tn##k = r_max(r_max(r_fma(bnx.k, L.idir.x, -L.oid.x), r_fma(bny.k, L.idir.y, -L.oid.y)),              \
-                  r_max(r_fma(bnz.k, L.idir.z, -L.oid.z), L.tmin));                                       \
+                  r_max(r_fma(bnz.k, L.idir.z, -L.oid.z), tmin));                                         \
   R tf##k = r_min(r_min(r_fma(bfx.k, L.idir.x, -L.oid.x), r_fma(bfy.k, L.idir.y, -L.oid.y)),              \
-                  r_min(r_fma(bfz.k, L.idir.z, -L.oid.z), L.tbest)) * fs;                                 \
+                  r_min(r_fma(bfz.k, L.idir.z, -L.oid.z), L.tbest));                                      \
+  if (sizeof(R) == 8) tf##k *= Lim<R>::far_scale();                                                       \
   tn##k = (tn##k <= tf##k) ? tn##k : INF;
     PTB_SLAB(x)
     PTB_SLAB(y)
@@ -345,51 +414,49 @@ __device__ __forceinline__ bool lane_step(Lane<R> &L, const SceneRef<R, SMEM> &S
     PTB_CSWAP(t0, c0, t1, c1)
     PTB_CSWAP(t2, c2, t3, c3)
     PTB_CSWAP(t0, c0, t2, c2)
-    PTB_CSWAP(t1, c1, t3, c3)
-    PTB_CSWAP(t1, c1, t2, c2)
-    if (t0 < INF) {
-      L.cur = c0;
-      if (t3 < INF && L.sp < stk_cap) {
-        sts_i32(stk_ref + L.sp * ref_stride, c3);
-        sts_r(stk_t + L.sp * t_stride, t3);
-        ++L.sp;
-      }
-      if (t2 < INF && L.sp < stk_cap) {
-        sts_i32(stk_ref + L.sp * ref_stride, c2);
-        sts_r(stk_t + L.sp * t_stride, t2);
-        ++L.sp;
-      }
-      if (t1 < INF && L.sp < stk_cap) {
-        sts_i32(stk_ref + L.sp * ref_stride, c1);
-        sts_r(stk_t + L.sp * t_stride, t1);
-        ++L.sp;
-      }
-    } else {
-      L.cur = TRAV_POP;
+    if (FULLSORT) {
+      PTB_CSWAP(t1, c1, t3, c3)
+      PTB_CSWAP(t1, c1, t2, c2)
+    }
+    L.cur = (t0 < INF) ? c0 : TRAV_POP;
+    // (t0 == INF implies t1..t3 == INF: nothing is pushed)
+    if (t3 < INF && (!CHECK || L.sp < sp_limit)) {
+      stk_store(L.sp, c3, t3);
+      L.sp += stride;
+    }
+    if (t2 < INF && (!CHECK || L.sp < sp_limit)) {
+      stk_store(L.sp, c2, t2);
+      L.sp += stride;
+    }
+    if (t1 < INF && (!CHECK || L.sp < sp_limit)) {
+      stk_store(L.sp, c1, t1);
+      L.sp += stride;
     }
   }
   if (L.cur < 0 && L.cur != TRAV_POP) {
     const unsigned code = ~(unsigned)L.cur;
     const int first = (int)(code & 0x3FFFFFFu);
     const int cnt = (int)((code >> 26) & 15u) + 1;
+    const R tmin = TMIN0 ? R(0) : L.tmin;
     if (((code >> 30) & 1u) == 0u) {
-      for (int i = 0; i < cnt; ++i)
-        sphere_test<R>(S.sphere(first + i), L.o, L.d, L.a, L.inv_a, L.tmin, L.tbest, L.best, first + i);
+#pragma unroll 1
+      for (int i = 0; i < cnt; ++i) sphere_test(S.sphere(first + i), L.o, L.d, L.a, L.inv_a, tmin, L.tbest, L.best, first + i);
     } else {
+#pragma unroll 1
       for (int i = 0; i < cnt; ++i)
-        tri_test<R>(S.tri(first + i, 0), S.tri(first + i, 1), S.tri(first + i, 2), L.o, L.d, L.tmin, L.tbest, L.best,
+        tri_test<R>(S.tri(first + i, 0), S.tri(first + i, 1), S.tri(first + i, 2), L.o, L.d, tmin, L.tbest, L.best,
                     (first + i) | (1 << 30));
     }
     L.cur = TRAV_POP;
   }
   if (L.cur == TRAV_POP) {
-    // pop, skipping subtrees that start beyond the current best hit
-    for (;;) {
-      if (L.sp == 0) return false;
-      --L.sp;
-      L.cur = lds_i32(stk_ref + L.sp * ref_stride);
-      if (lds_r(stk_t + L.sp * t_stride, R()) <= L.tbest) break;
-    }
+    // pop, skipping subtrees that start beyond the current best hit; the sentinel (t = -inf) always stops it
+    R t;
+    do {
+      L.sp -= stride;
+      stk_load(L.sp, L.cur, t);
+    } while (t > L.tbest);
+    if (L.cur == TRAV_DONE) return false;  // (lane_init resets sp before the lane is used again)
   }
   return true;
 }
@@ -488,8 +555,24 @@ __global__ void __launch_bounds__(256) k_raygen(RenderConst rc, const int32_t *_
 //   miss -> background * attenuation added into the per-pixel sums (integrator.ml:36)
 //   hit  -> appended to the queue of its material kind, warp-aggregated with __ballot_sync/__popc
 // MODE 0: pipeline.  MODE 1: intersect only (t and caller primitive index per ray).
+//
+// Registers are the scarce resource (1024 threads per SM leave 64 each), so everything the traversal loop
+// does not touch lives in shared memory: the ray's payload (attenuation, pixel, R2 offset) is parked in a
+// per-thread slot at refill and read back at flush, and the warp-uniform bookkeeping (claimed input
+// range, open output segments, statistics) sits in a per-warp record.
+//
+// Dynamic shared memory: [scene (SMEM)] [stack: stack_cap x threads x ENTRY] [payload: threads x (Vec4 + R)]
+//                        [warp records: warps x WS_WORDS x 4 B]
+constexpr unsigned WS_NEXT = 0, WS_END = 1, WS_FETCHED = 2, WS_SEG = 3 /* base,fill x 3 kinds */, WS_WORDS = 12;
+
+// dynamic shared memory per thread besides the staged scene: stack + payload slot + share of the warp record
+template <class R>
+__host__ __device__ constexpr size_t trace_smem_per_thread(int stack_cap) {
+  return (size_t)stack_cap * 2u * sizeof(R) + sizeof(Vec4<R>) + sizeof(R) + (WS_WORDS * 4u + 31u) / 32u;
+}
+
 template <class R, int MODE, bool SMEM>
-__global__ void __launch_bounds__(SMEM ? 1024 : 256, 1)
+__global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, 1)
     k_trace(DScene<R> sc, Queue<R> rays, const unsigned *__restrict__ nseg_ptr, unsigned nseg_imm,
             unsigned *__restrict__ cursor, int refill_below, Queue<R> q0, Queue<R> q1, Queue<R> q2,
             unsigned *__restrict__ nseg_mat, unsigned *__restrict__ n_traced, int enqueue_hits, R *__restrict__ sums,
@@ -498,13 +581,10 @@ __global__ void __launch_bounds__(SMEM ? 1024 : 256, 1)
   const unsigned nseg = nseg_ptr ? *nseg_ptr : nseg_imm;  // segments in the input ray queue
   const int tid = threadIdx.x;
   const unsigned lane = tid & 31;
-  const unsigned lt_mask = (1u << lane) - 1u;
   // claim granularity: a quarter, half or whole segment, so that a small launch (late bounces) still
   // spreads over every persistent warp and a big one pays one cursor atomic per 128 rays
   const unsigned per_warp = nseg * (unsigned)SEG / (gridDim.x * (blockDim.x >> 5));
   const unsigned claim_shift = per_warp >= 512u ? 0u : (per_warp >= 256u ? 1u : 2u);  // units per segment = 1 << shift
-  const unsigned claim = (unsigned)SEG >> claim_shift;
-  const unsigned nunits = nseg << claim_shift;
   const unsigned smem_base = (unsigned)__cvta_generic_to_shared(smem);
   SceneRef<R, SMEM> S;
   S.g_nodes = reinterpret_cast<const char *>(sc.nodes), S.g_spheres = sc.spheres, S.g_tris = sc.tris;
@@ -528,24 +608,34 @@ __global__ void __launch_bounds__(SMEM ? 1024 : 256, 1)
     S.s_nodes = smem_base, S.s_spheres = smem_base + nb, S.s_tris = smem_base + nb + sb;
     S.s_kinds = smem_base + nb + sb + tb;
     __syncthreads();
+    // the shared-memory sphere records carry r^2 (what the intersection test needs)
+    Vec4<R> *ssph = reinterpret_cast<Vec4<R> *>(smem + nb);
+    for (unsigned i = tid; i < (unsigned)sc.n_spheres; i += blockDim.x) ssph[i].w *= ssph[i].w;
+    __syncthreads();
   }
-  const unsigned ref_stride = blockDim.x * 4u, t_stride = blockDim.x * (unsigned)sizeof(R);
-  const unsigned stk_ref = smem_base + scene_bytes + (unsigned)tid * 4u;
-  const unsigned stk_t = smem_base + scene_bytes + (unsigned)sc.stack_cap * ref_stride + (unsigned)tid * (unsigned)sizeof(R);
+  // traversal stack: stack[level][thread], entry = (ref, t_near); level 0 is the sentinel
+  constexpr unsigned ENTRY = 2u * (unsigned)sizeof(R);
+  const unsigned stride = blockDim.x * ENTRY;
+  const unsigned stk0 = smem_base + scene_bytes + (unsigned)tid * ENTRY;
+  stk_store(stk0, TRAV_DONE, -Lim<R>::inf());
+  const unsigned sp0 = stk0 + stride;
+  const unsigned sp_limit = stk0 + (unsigned)sc.stack_cap * stride;  // entries [1, stack_cap) hold pushes
+  // per-thread payload slot and per-warp record
+  const unsigned pay_base = smem_base + scene_bytes + (unsigned)sc.stack_cap * stride;
+  const unsigned pay_v = pay_base + (unsigned)tid * (unsigned)sizeof(Vec4<R>);
+  const unsigned pay_r = pay_base + blockDim.x * (unsigned)sizeof(Vec4<R>) + (unsigned)tid * (unsigned)sizeof(R);
+  const unsigned ws = pay_base + blockDim.x * (unsigned)(sizeof(Vec4<R>) + sizeof(R)) + ((unsigned)tid >> 5) * (WS_WORDS * 4u);
+  if (lane < WS_WORDS) sts_i32(ws + lane * 4u, (lane >= WS_SEG && ((lane - WS_SEG) & 1u) == 0u) ? (int)NO_SEG : 0);
+  __syncwarp();
 
   Lane<R> L;
-  L.cur = TRAV_POP, L.sp = 0, L.best = -1, L.tbest = R(0);
+  L.cur = TRAV_POP, L.sp = sp0, L.best = -1, L.tbest = R(0);
+  L.onx = L.ony = L.onz = 0u;
   L.o = L.d = {R(0), R(0), R(1)};
   bool has_ray = false;  // this lane is traversing
   bool done = false;     // this lane holds a finished ray whose result is not flushed yet
-  unsigned ray_i = 0;
-  R a_w = R(0), b_w = R(0);           // the two integer payload words of the ray (pixel, offset)
-  V3<R> attn = {R(0), R(0), R(0)};    // the ray's attenuation (queue word C), carried in registers
-  unsigned chunk_next = 0, chunk_end = 0;  // warp-uniform: the claimed input segment [next, end)
-  bool more = true;                        // warp-uniform: the queue may still hold segments
-  unsigned fetched = 0;                    // warp-uniform: rays this warp has traced (statistics)
-  // warp-uniform: this warp's open segment in each material queue
-  unsigned sb0 = NO_SEG, sf0 = 0, sb1 = NO_SEG, sf1 = 0, sb2 = NO_SEG, sf2 = 0;
+  unsigned ray_i = 0;    // MODE 1: where the result goes
+  bool more = true;      // warp-uniform: the queue may still hold segments
 
   for (;;) {
     // ---------------- flush finished lanes (whole warp, convergent; no global loads) ------------
@@ -557,37 +647,54 @@ __global__ void __launch_bounds__(SMEM ? 1024 : 256, 1)
           out_prim[ray_i] = L.best < 0 ? -1 : ((L.best >> 30) & 1 ? sc.n_spheres + sc.tri_id[slot] : sc.sphere_id[slot]);
         }
       } else {
+        const unsigned lt_mask = (1u << lane) - 1u;
         int kind = -1;
+        Vec4<R> pv = {R(0), R(0), R(0), R(0)};  // (attenuation, pixel)
         if (done) {
+          pv = lds_vec4(pay_v, R());
           if (L.best < 0) {
             // integrator.ml:36: emit0 + attn0 * background ray (emit0 == 0: Material.emit is black)
             const V3<R> bg = background(sc, L.d);
-            const int pixel = r2i(a_w);
-            atomicAdd(&sums[3 * (size_t)pixel + 0], attn.x * bg.x);
-            atomicAdd(&sums[3 * (size_t)pixel + 1], attn.y * bg.y);
-            atomicAdd(&sums[3 * (size_t)pixel + 2], attn.z * bg.z);
+            const int pixel = r2i(pv.w);
+            atomicAdd(&sums[3 * (size_t)pixel + 0], pv.x * bg.x);
+            atomicAdd(&sums[3 * (size_t)pixel + 1], pv.y * bg.y);
+            atomicAdd(&sums[3 * (size_t)pixel + 2], pv.z * bg.z);
           } else if (enqueue_hits) {
             kind = S.kind(L.best, sc.n_spheres);
           }
         }
         // per-material segmented queues: no global atomic unless a segment fills up
+        unsigned sb0 = (unsigned)lds_i32(ws + (WS_SEG + 0u) * 4u), sf0 = (unsigned)lds_i32(ws + (WS_SEG + 1u) * 4u);
+        unsigned sb1 = (unsigned)lds_i32(ws + (WS_SEG + 2u) * 4u), sf1 = (unsigned)lds_i32(ws + (WS_SEG + 3u) * 4u);
+        unsigned sb2 = (unsigned)lds_i32(ws + (WS_SEG + 4u) * 4u), sf2 = (unsigned)lds_i32(ws + (WS_SEG + 5u) * 4u);
+        __syncwarp();
         const unsigned d0 = seg_append(kind == 0, sb0, sf0, &nseg_mat[0], q0.seg_count, lane, lt_mask);
         const unsigned d1 = seg_append(kind == 1, sb1, sf1, &nseg_mat[1], q1.seg_count, lane, lt_mask);
         const unsigned d2 = seg_append(kind == 2, sb2, sf2, &nseg_mat[2], q2.seg_count, lane, lt_mask);
+        if (lane == 0) {
+          sts_i32(ws + (WS_SEG + 0u) * 4u, (int)sb0), sts_i32(ws + (WS_SEG + 1u) * 4u, (int)sf0);
+          sts_i32(ws + (WS_SEG + 2u) * 4u, (int)sb1), sts_i32(ws + (WS_SEG + 3u) * 4u, (int)sf1);
+          sts_i32(ws + (WS_SEG + 4u) * 4u, (int)sb2), sts_i32(ws + (WS_SEG + 5u) * 4u, (int)sf2);
+        }
         if (kind >= 0) {
           const unsigned dst = kind == 0 ? d0 : (kind == 1 ? d1 : d2);
           const Queue<R> &q = (kind == 0) ? q0 : (kind == 1 ? q1 : q2);
-          q.A[dst] = {r_fma(L.tbest, L.d.x, L.o.x), r_fma(L.tbest, L.d.y, L.o.y), r_fma(L.tbest, L.d.z, L.o.z), a_w};
-          q.B[dst] = {L.d.x, L.d.y, L.d.z, b_w};
-          q.C[dst] = {attn.x, attn.y, attn.z, i2r(L.best, R())};
+          q.A[dst] = {r_fma(L.tbest, L.d.x, L.o.x), r_fma(L.tbest, L.d.y, L.o.y), r_fma(L.tbest, L.d.z, L.o.z), pv.w};
+          q.B[dst] = {L.d.x, L.d.y, L.d.z, lds_r(pay_r, R())};
+          q.C[dst] = {pv.x, pv.y, pv.z, i2r(L.best, R())};
         }
+        __syncwarp();
       }
       done = false;
     }
     // ---------------- refill idle lanes from the queue (one parallel round trip) ----------------
-    unsigned idle = __ballot_sync(0xffffffffu, !has_ray);
+    const unsigned idle = __ballot_sync(0xffffffffu, !has_ray);
     if (more && idle) {
+      unsigned chunk_next = (unsigned)lds_i32(ws + WS_NEXT * 4u), chunk_end = (unsigned)lds_i32(ws + WS_END * 4u);
+      __syncwarp();
       if (chunk_next >= chunk_end) {  // claim the next unit (segment or part of one) of the input queue
+        const unsigned claim = (unsigned)SEG >> claim_shift;
+        const unsigned nunits = nseg << claim_shift;
         unsigned u = 0, c = 0;
         if (lane == 0) {
           u = atomicAdd(cursor, 1u);
@@ -608,22 +715,26 @@ __global__ void __launch_bounds__(SMEM ? 1024 : 256, 1)
         const unsigned want = (unsigned)__popc(idle);
         const unsigned avail = chunk_end - chunk_next;
         const unsigned take = want < avail ? want : avail;
-        const unsigned rank = (unsigned)__popc(idle & lt_mask);
+        const unsigned rank = (unsigned)__popc(idle & ((1u << lane) - 1u));
         if (!has_ray && rank < take) {
           ray_i = chunk_next + rank;
           const Vec4<R> A = rays.A[ray_i], B = rays.B[ray_i];
           if (MODE == 0) {
             const Vec4<R> C = rays.C[ray_i];
-            attn = {C.x, C.y, C.z};
+            // park the payload: (attenuation, pixel) and the R2 offset
+            const Vec4<R> pv = {C.x, C.y, C.z, A.w};
+            sts_vec4(pay_v, pv);
+            sts_r(pay_r, B.w);
           }
-          a_w = A.w, b_w = B.w;
           lane_init<R>(L, V3<R>{A.x, A.y, A.z}, V3<R>{B.x, B.y, B.z}, (MODE == 0) ? R(0) : tmin_arg,
-                       (MODE == 0) ? Lim<R>::tmax() : tmax_arg);
+                       (MODE == 0) ? Lim<R>::tmax() : tmax_arg, sp0);
           has_ray = true;
         }
         chunk_next += take;
-        fetched += take;
+        if (lane == 0 && MODE == 0) sts_i32(ws + WS_FETCHED * 4u, lds_i32(ws + WS_FETCHED * 4u) + (int)take);
       }
+      if (lane == 0) sts_i32(ws + WS_NEXT * 4u, (int)chunk_next), sts_i32(ws + WS_END * 4u, (int)chunk_end);
+      __syncwarp();
     }
     const unsigned active = __ballot_sync(0xffffffffu, has_ray);
     if (active == 0u) {
@@ -634,7 +745,7 @@ __global__ void __launch_bounds__(SMEM ? 1024 : 256, 1)
     const int keep = more ? refill_below : 1;
     do {
       if (has_ray) {
-        if (!lane_step<R, SMEM>(L, S, stk_ref, stk_t, ref_stride, t_stride, sc.stack_cap)) {
+        if (!lane_step<R, SMEM, MODE == 0, sizeof(R) == 8, !SMEM>(L, S, stride, sp_limit)) {
           has_ray = false;
           done = true;
         }
@@ -642,9 +753,11 @@ __global__ void __launch_bounds__(SMEM ? 1024 : 256, 1)
     } while (__popc(__ballot_sync(0xffffffffu, has_ray)) >= keep);
   }
   if (MODE == 0) {
-    seg_close(sb0, sf0, q0.seg_count, lane);
-    seg_close(sb1, sf1, q1.seg_count, lane);
-    seg_close(sb2, sf2, q2.seg_count, lane);
+    __syncwarp();
+    seg_close((unsigned)lds_i32(ws + (WS_SEG + 0u) * 4u), (unsigned)lds_i32(ws + (WS_SEG + 1u) * 4u), q0.seg_count, lane);
+    seg_close((unsigned)lds_i32(ws + (WS_SEG + 2u) * 4u), (unsigned)lds_i32(ws + (WS_SEG + 3u) * 4u), q1.seg_count, lane);
+    seg_close((unsigned)lds_i32(ws + (WS_SEG + 4u) * 4u), (unsigned)lds_i32(ws + (WS_SEG + 5u) * 4u), q2.seg_count, lane);
+    const unsigned fetched = (unsigned)lds_i32(ws + WS_FETCHED * 4u);
     if (lane == 0 && fetched) atomicAdd(n_traced, fetched);
   }
 }

@@ -268,8 +268,10 @@ static DScene<R> make_dscene(ptb_scene *s, size_t *scene_bytes_out) {
   sc.n_tris = (int)s->bvh.tri_order.size();
   size_t bytes = (size_t)sc.n_nodes * sizeof(Node4<R>) + (size_t)sc.n_spheres * sizeof(Vec4<R>) +
                  (size_t)sc.n_tris * 3 * sizeof(Vec4<R>) + (((size_t)sc.n_spheres + sc.n_tris + 15) / 16) * 16;
-  sc.scene_in_smem = bytes <= 100 * 1024 ? 1 : 0;
-  sc.stack_cap = std::min(std::max(s->bvh.max_stack, 4), 96);
+  // entry 0 of the traversal stack is the sentinel.  A tree whose worst case fits gets an unchecked stack
+  // (shared-memory scenes); deeper trees run the global-memory variant, which guards every push.
+  sc.stack_cap = std::min(std::max(s->bvh.max_stack + 1, 4), 97);
+  sc.scene_in_smem = (bytes <= 100 * 1024 && s->bvh.max_stack + 1 <= sc.stack_cap) ? 1 : 0;
   sc.bg_kind = s->host.bg_kind;
   for (int i = 0; i < 3; ++i) sc.bg0[i] = (R)s->host.bg0[i], sc.bg1[i] = (R)s->host.bg1[i];
   *scene_bytes_out = sc.scene_in_smem ? bytes : 0;
@@ -286,10 +288,10 @@ struct TraceLaunch {
 // blocks at whatever occupancy the stack allows.
 template <class R, int MODE>
 static int trace_config(DeviceState *d, const DScene<R> &sc, size_t scene_bytes, TraceLaunch *tl) {
-  const size_t per_thread = (size_t)sc.stack_cap * (sizeof(int) + sizeof(R));
+  const size_t per_thread = trace_smem_per_thread<R>(sc.stack_cap);  // stack + payload slot + warp record
   tl->scene_smem = sc.scene_in_smem != 0;
   if (tl->scene_smem) {
-    tl->block = 1024;
+    tl->block = sizeof(R) == 8 ? 512 : 1024;  // = the kernel's __launch_bounds__
     while (tl->block > 128 && scene_bytes + per_thread * tl->block > d->smem_optin) tl->block -= 128;
     tl->smem = scene_bytes + per_thread * tl->block;
     if (tl->smem > d->smem_optin) return fail(PTB_E_NOMEM, "trace: scene + stack do not fit shared memory");
