@@ -10,6 +10,7 @@
 // type bit in the leaf code).  Closest-hit results do not depend on the tree shape.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <queue>
@@ -33,6 +34,22 @@ struct BinNode {
 };
 
 constexpr int NBINS = 32;
+
+// builder tuning (overridable for experiments: PTB_BVH_LEAF, PTB_BVH_CT, PTB_BVH_MINLEAF)
+struct Tune {
+  int leaf_max = LEAF_MAX;  // primitives per leaf (<= 16: the leaf code has 4 count bits)
+  double ct = 1.2;          // cost of visiting a 4-wide node, in primitive tests
+  int min_leaf = 2;         // ranges this small always become a leaf
+  Tune() {
+    if (const char *e = std::getenv("PTB_BVH_LEAF")) leaf_max = std::min(16, std::max(1, std::atoi(e)));
+    if (const char *e = std::getenv("PTB_BVH_CT")) ct = std::atof(e);
+    if (const char *e = std::getenv("PTB_BVH_MINLEAF")) min_leaf = std::max(1, std::atoi(e));
+  }
+};
+static const Tune &tune() {
+  static Tune t;
+  return t;
+}
 
 struct BinaryBuilder {
   std::vector<PrimRef> &prims;
@@ -62,7 +79,7 @@ struct BinaryBuilder {
       nodes[me].type = type;
       return me;
     };
-    if (n <= LEAF_MAX && n <= 2) return make_leaf();
+    if (n <= tune().leaf_max && n <= tune().min_leaf) return make_leaf();
     // binned SAH over the three axes
     double best_cost = 1e300;
     int best_axis = -1, best_split = -1;
@@ -102,17 +119,17 @@ struct BinaryBuilder {
     }
     if (best_axis < 0) {
       // all centroids coincide: split by index while the leaf is too big
-      if (n <= LEAF_MAX) return make_leaf();
+      if (n <= tune().leaf_max) return make_leaf();
       int mid = lo + n / 2;
       int l = build(lo, mid);
       int r = build(mid, hi);
       nodes[me].lhs = l, nodes[me].rhs = r;
       return me;
     }
-    if (n <= LEAF_MAX) {
+    if (n <= tune().leaf_max) {
       // leaf cost n * Ci vs split cost Ct + sum; Ci = 1, Ct = 1.2 (a 4-wide node visit costs a few
       // primitive tests on the device)
-      double split_cost = 1.2 + best_cost / std::max(box.area(), 1e-300);
+      double split_cost = tune().ct + best_cost / std::max(box.area(), 1e-300);
       if (split_cost >= (double)n) return make_leaf();
     }
     double ext = cbox.mx[best_axis] - cbox.mn[best_axis];

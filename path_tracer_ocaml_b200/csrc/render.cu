@@ -312,6 +312,14 @@ static int trace_config(DeviceState *d, const DScene<R> &sc, size_t scene_bytes,
   }
   return PTB_OK;
 }
+static int leaf_min() {
+  static int v = -1;
+  if (v < 0) {
+    v = 8;
+    if (const char *e = std::getenv("PTB_LEAFMIN")) v = std::min(32, std::max(1, std::atoi(e)));
+  }
+  return v;
+}
 static int refill_below() {
   static int v = -1;
   if (v < 0) {
@@ -325,11 +333,11 @@ static void launch_trace(const TraceLaunch &tl, cudaStream_t st, const DScene<R>
                          const unsigned *nseg_ptr, unsigned nseg_imm, unsigned *cursor, Queue<R> *mq, unsigned *nseg_mat,
                          unsigned *n_traced, int enqueue_hits, R *sums, R tmin, R tmax, R *out_t, int32_t *out_prim) {
   if (tl.scene_smem)
-    k_trace<R, MODE, true><<<tl.grid, tl.block, tl.smem, st>>>(sc, rays, nseg_ptr, nseg_imm, cursor, refill_below(), mq[0],
+    k_trace<R, MODE, true><<<tl.grid, tl.block, tl.smem, st>>>(sc, rays, nseg_ptr, nseg_imm, cursor, refill_below(), leaf_min(), mq[0],
                                                                mq[1], mq[2], nseg_mat, n_traced, enqueue_hits, sums, tmin,
                                                                tmax, out_t, out_prim);
   else
-    k_trace<R, MODE, false><<<tl.grid, tl.block, tl.smem, st>>>(sc, rays, nseg_ptr, nseg_imm, cursor, refill_below(), mq[0],
+    k_trace<R, MODE, false><<<tl.grid, tl.block, tl.smem, st>>>(sc, rays, nseg_ptr, nseg_imm, cursor, refill_below(), leaf_min(), mq[0],
                                                                 mq[1], mq[2], nseg_mat, n_traced, enqueue_hits, sums, tmin,
                                                                 tmax, out_t, out_prim);
 }

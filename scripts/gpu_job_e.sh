@@ -1,0 +1,6 @@
+#!/bin/bash
+set -x
+PTB_BATCH=8388608 python bench.py --spp 2 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/plain.log 2>&1 &&
+PTB_BATCH=8388608 ncu --set full --clock-control none --import-source on -k regex:'k_trace' -s 0 -c 2 \
+   -f -o gpurun_out/trace_v5 python bench.py --spp 2 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_v5.log 2>&1
+echo done
