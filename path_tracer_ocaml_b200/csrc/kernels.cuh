@@ -528,26 +528,41 @@ __device__ __forceinline__ void seg_close(unsigned seg_base, unsigned seg_fill, 
 // kernels
 // =================================================================================================
 
+// Camera ray of sample `k` of a batch (integrator.ml:96-105, camera.ml:93-102): the sample enumeration is
+// pass-major over this rank's pixel list; R2 jitter, cx, cy and the un-normalized direction are float64 with
+// un-fused operations (bit-exact against the reference).  Shared by k_raygen and by the bounce-0 traversal
+// kernel, which generates its rays in registers instead of reading them from a queue.
+struct GenConst {
+  int32_t W, spp, npix, pass0, i0, pad;
+  double llx, lly, vx, vy, widthf, heightf, alpha0, alpha1;
+  const int32_t *pixel_list;
+};
+__device__ __forceinline__ void camera_sample(const GenConst &g, unsigned k, int &pixel, int &offset, double &cx,
+                                              double &cy, double &ddx, double &ddy) {
+  const unsigned idx = (unsigned)g.i0 + k;  // < npix + batch size < 2^31 (checked on the host)
+  const unsigned q = idx / (unsigned)g.npix;
+  const int i = (int)(idx - q * (unsigned)g.npix);
+  pixel = __ldg(g.pixel_list + i);
+  const int gy = pixel / g.W, gx = pixel - gy * g.W;
+  offset = pixel + (g.pass0 + (int)q) * g.spp;  // integrator.ml:98 (sic: pass * samples_per_pixel)
+  const double dx = r2_sample(g.alpha0, offset), dy = r2_sample(g.alpha1, offset);
+  cx = __dmul_rn(__dadd_rn((double)gx, dx), g.widthf);                    // integrator.ml:104
+  cy = __dsub_rn(1.0, __dmul_rn(__dadd_rn((double)gy, dy), g.heightf));   // integrator.ml:105
+  ddx = __dadd_rn(g.llx, __dmul_rn(g.vx, cx));                            // camera.ml:96-97
+  ddy = __dadd_rn(g.lly, __dmul_rn(g.vy, cy));
+}
+
 // Stage 1 — camera rays.  One thread per sample of the batch [first, first+n) of this rank's
 // enumeration (pass-major over the rank's pixel list, which is in tile order).
 template <class R>
-__global__ void __launch_bounds__(256) k_raygen(RenderConst rc, const int32_t *__restrict__ pixel_list, int pass0,
-                                                int i0, unsigned n, Queue<R> out, double *__restrict__ dbg_cx,
+__global__ void __launch_bounds__(256) k_raygen(GenConst g, unsigned n, Queue<R> out, double *__restrict__ dbg_cx,
                                                 double *__restrict__ dbg_cy) {
   for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-    long long idx = (long long)i0 + k;
-    int pass = pass0 + (int)(idx / rc.npix);
-    int i = (int)(idx % rc.npix);
-    int pixel = pixel_list[i];
-    int gy = pixel / rc.W, gx = pixel - gy * rc.W;
-    int offset = pixel + pass * rc.spp;  // integrator.ml:98 (sic: pass * samples_per_pixel)
-    double dx = r2_sample(rc.alpha[0], offset), dy = r2_sample(rc.alpha[1], offset);
-    double cx = __dmul_rn(__dadd_rn((double)gx, dx), rc.widthf);                    // integrator.ml:104
-    double cy = __dsub_rn(1.0, __dmul_rn(__dadd_rn((double)gy, dy), rc.heightf));   // integrator.ml:105
+    int pixel, offset;
+    double cx, cy, ddx, ddy;
+    camera_sample(g, k, pixel, offset, cx, cy, ddx, ddy);
     if (dbg_cx) dbg_cx[k] = cx;
     if (dbg_cy) dbg_cy[k] = cy;
-    double ddx = __dadd_rn(rc.llx, __dmul_rn(rc.vx, cx));  // camera.ml:96-97
-    double ddy = __dadd_rn(rc.lly, __dmul_rn(rc.vy, cy));
     V3<R> dir = normalize(V3<R>{R(ddx), R(ddy), R(-1)});
     out.A[k] = {R(0), R(0), R(0), i2r(pixel, R())};
     out.B[k] = {dir.x, dir.y, dir.z, i2r(offset, R())};
@@ -579,9 +594,11 @@ __host__ __device__ constexpr size_t trace_smem_per_thread(int stack_cap) {
   return (size_t)stack_cap * 2u * sizeof(R) + sizeof(Vec4<R>) + sizeof(R) + (WS_WORDS * 4u + 31u) / 32u;
 }
 
-template <class R, int MODE, bool SMEM>
+// GEN: bounce 0 — the rays are the camera samples [0, gen_n) of the batch, generated in registers
+// (camera_sample) instead of being read from `rays`.
+template <class R, int MODE, bool SMEM, bool GEN>
 __global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, 1)
-    k_trace(DScene<R> sc, Queue<R> rays, const unsigned *__restrict__ nseg_ptr, unsigned nseg_imm,
+    k_trace(DScene<R> sc, GenConst gen, unsigned gen_n, Queue<R> rays, const unsigned *__restrict__ nseg_ptr, unsigned nseg_imm,
             unsigned *__restrict__ cursor, int refill_below, int leaf_min, Queue<R> q0, Queue<R> q1, Queue<R> q2,
             unsigned *__restrict__ nseg_mat, unsigned *__restrict__ n_traced, int enqueue_hits, R *__restrict__ sums,
             R tmin_arg, R tmax_arg, R *__restrict__ out_t, int32_t *__restrict__ out_prim) {
@@ -705,7 +722,14 @@ __global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, 1)
         unsigned u = 0, c = 0;
         if (lane == 0) {
           u = atomicAdd(cursor, 1u);
-          if (u < nunits) c = (unsigned)rays.seg_count[u >> claim_shift];
+          if (u < nunits) {
+            if (GEN) {
+              const unsigned s0 = (u >> claim_shift) * (unsigned)SEG;
+              c = gen_n - s0 < (unsigned)SEG ? gen_n - s0 : (unsigned)SEG;
+            } else {
+              c = (unsigned)rays.seg_count[u >> claim_shift];
+            }
+          }
         }
         u = __shfl_sync(0xffffffffu, u, 0);
         c = __shfl_sync(0xffffffffu, c, 0);
@@ -725,16 +749,27 @@ __global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, 1)
         const unsigned rank = (unsigned)__popc(idle & ((1u << lane) - 1u));
         if (L.cur == TRAV_IDLE && rank < take) {
           ray_i = chunk_next + rank;
-          const Vec4<R> A = rays.A[ray_i], B = rays.B[ray_i];
-          if (MODE == 0) {
-            const Vec4<R> C = rays.C[ray_i];
-            // park the payload: (attenuation, pixel) and the R2 offset
-            const Vec4<R> pv = {C.x, C.y, C.z, A.w};
+          if (GEN) {
+            int pixel, offset;
+            double cx, cy, ddx, ddy;
+            camera_sample(gen, ray_i, pixel, offset, cx, cy, ddx, ddy);
+            const V3<R> dir = normalize(V3<R>{R(ddx), R(ddy), R(-1)});
+            const Vec4<R> pv = {R(1), R(1), R(1), i2r(pixel, R())};
             sts_vec4(pay_v, pv);
-            sts_r(pay_r, B.w);
+            sts_r(pay_r, i2r(offset, R()));
+            lane_init<R>(L, V3<R>{R(0), R(0), R(0)}, dir, R(0), Lim<R>::tmax(), sp0);
+          } else {
+            const Vec4<R> A = rays.A[ray_i], B = rays.B[ray_i];
+            if (MODE == 0) {
+              const Vec4<R> C = rays.C[ray_i];
+              // park the payload: (attenuation, pixel) and the R2 offset
+              const Vec4<R> pv = {C.x, C.y, C.z, A.w};
+              sts_vec4(pay_v, pv);
+              sts_r(pay_r, B.w);
+            }
+            lane_init<R>(L, V3<R>{A.x, A.y, A.z}, V3<R>{B.x, B.y, B.z}, (MODE == 0) ? R(0) : tmin_arg,
+                         (MODE == 0) ? Lim<R>::tmax() : tmax_arg, sp0);
           }
-          lane_init<R>(L, V3<R>{A.x, A.y, A.z}, V3<R>{B.x, B.y, B.z}, (MODE == 0) ? R(0) : tmin_arg,
-                       (MODE == 0) ? Lim<R>::tmax() : tmax_arg, sp0);
         }
         chunk_next += take;
         if (lane == 0 && MODE == 0) sts_i32(ws + WS_FETCHED * 4u, lds_i32(ws + WS_FETCHED * 4u) + (int)take);

@@ -253,6 +253,16 @@ static int fill_render_const(const ptb_params &p, int npix, RenderConst *rc) {
   return PTB_OK;
 }
 
+static GenConst make_gen(const RenderConst &rc, const int32_t *pixel_list, int pass0, int i0) {
+  GenConst g;
+  std::memset(&g, 0, sizeof g);
+  g.W = rc.W, g.spp = rc.spp, g.npix = rc.npix, g.pass0 = pass0, g.i0 = i0;
+  g.llx = rc.llx, g.lly = rc.lly, g.vx = rc.vx, g.vy = rc.vy, g.widthf = rc.widthf, g.heightf = rc.heightf;
+  g.alpha0 = rc.alpha[0], g.alpha1 = rc.alpha[1];
+  g.pixel_list = pixel_list;
+  return g;
+}
+
 template <class R>
 static DScene<R> make_dscene(ptb_scene *s, size_t *scene_bytes_out) {
   DeviceState *d = s->dev;
@@ -295,18 +305,22 @@ static int trace_config(DeviceState *d, const DScene<R> &sc, size_t scene_bytes,
     while (tl->block > 128 && scene_bytes + per_thread * tl->block > d->smem_optin) tl->block -= 128;
     tl->smem = scene_bytes + per_thread * tl->block;
     if (tl->smem > d->smem_optin) return fail(PTB_E_NOMEM, "trace: scene + stack do not fit shared memory");
-    CK(cudaFuncSetAttribute(k_trace<R, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl->smem));
+    CK(cudaFuncSetAttribute(k_trace<R, MODE, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl->smem));
+    if (MODE == 0)
+      CK(cudaFuncSetAttribute(k_trace<R, MODE, true, MODE == 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl->smem));
     int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<R, MODE, true>, tl->block, tl->smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<R, MODE, true, false>, tl->block, tl->smem));
     if (per_sm < 1) return fail(PTB_E_CUDA, "trace: kernel cannot be resident");
     tl->grid = d->sm_count * per_sm;
   } else {
     tl->block = 256;
     while (tl->block > 64 && per_thread * tl->block > d->smem_optin / 2) tl->block /= 2;
     tl->smem = per_thread * tl->block;
-    CK(cudaFuncSetAttribute(k_trace<R, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl->smem));
+    CK(cudaFuncSetAttribute(k_trace<R, MODE, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl->smem));
+    if (MODE == 0)
+      CK(cudaFuncSetAttribute(k_trace<R, MODE, false, MODE == 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl->smem));
     int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<R, MODE, false>, tl->block, tl->smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<R, MODE, false, false>, tl->block, tl->smem));
     if (per_sm < 1) return fail(PTB_E_CUDA, "trace: kernel cannot be resident");
     tl->grid = d->sm_count * per_sm;
   }
@@ -328,18 +342,31 @@ static int refill_below() {
   }
   return v;
 }
+// gen != nullptr: bounce 0, the kernel generates the camera rays [0, gen_n) of the batch itself
 template <class R, int MODE>
-static void launch_trace(const TraceLaunch &tl, cudaStream_t st, const DScene<R> &sc, Queue<R> rays,
-                         const unsigned *nseg_ptr, unsigned nseg_imm, unsigned *cursor, Queue<R> *mq, unsigned *nseg_mat,
-                         unsigned *n_traced, int enqueue_hits, R *sums, R tmin, R tmax, R *out_t, int32_t *out_prim) {
-  if (tl.scene_smem)
-    k_trace<R, MODE, true><<<tl.grid, tl.block, tl.smem, st>>>(sc, rays, nseg_ptr, nseg_imm, cursor, refill_below(), leaf_min(), mq[0],
-                                                               mq[1], mq[2], nseg_mat, n_traced, enqueue_hits, sums, tmin,
-                                                               tmax, out_t, out_prim);
-  else
-    k_trace<R, MODE, false><<<tl.grid, tl.block, tl.smem, st>>>(sc, rays, nseg_ptr, nseg_imm, cursor, refill_below(), leaf_min(), mq[0],
-                                                                mq[1], mq[2], nseg_mat, n_traced, enqueue_hits, sums, tmin,
-                                                                tmax, out_t, out_prim);
+static void launch_trace(const TraceLaunch &tl, cudaStream_t st, const DScene<R> &sc, const GenConst *gen, unsigned gen_n,
+                         Queue<R> rays, const unsigned *nseg_ptr, unsigned nseg_imm, unsigned *cursor, Queue<R> *mq,
+                         unsigned *nseg_mat, unsigned *n_traced, int enqueue_hits, R *sums, R tmin, R tmax, R *out_t,
+                         int32_t *out_prim) {
+  GenConst g;
+  std::memset(&g, 0, sizeof g);
+  if (gen) g = *gen;
+#define PTB_LAUNCH(SM, GN)                                                                                             \
+  k_trace<R, MODE, SM, GN><<<tl.grid, tl.block, tl.smem, st>>>(sc, g, gen_n, rays, nseg_ptr, nseg_imm, cursor,        \
+                                                               refill_below(), leaf_min(), mq[0], mq[1], mq[2], nseg_mat, \
+                                                               n_traced, enqueue_hits, sums, tmin, tmax, out_t, out_prim)
+  if (MODE == 0 && gen) {
+    if (tl.scene_smem)
+      PTB_LAUNCH(true, MODE == 0);
+    else
+      PTB_LAUNCH(false, MODE == 0);
+  } else {
+    if (tl.scene_smem)
+      PTB_LAUNCH(true, false);
+    else
+      PTB_LAUNCH(false, false);
+  }
+#undef PTB_LAUNCH
 }
 
 static size_t batch_capacity() {
@@ -386,9 +413,8 @@ static int render_impl(ptb_scene *s, const ptb_params &p, R *d_sums, cudaStream_
     const unsigned n = (unsigned)std::min<long long>((long long)NB, total - first);
     k_batch_ctl<<<1, 128, 0, st>>>(ctl, n, p.max_bounces);
     const int pass0 = (int)(first / pl->npix), i0 = (int)(first % pl->npix);
-    const int rg_grid = (int)std::min<long long>(((long long)n + 255) / 256, (long long)d->sm_count * 8);
-    k_raygen<R><<<rg_grid, 256, 0, st>>>(rcst, pl->pixel_list, pass0, i0, n, w.rays, nullptr, nullptr);
-    launches += 2;
+    const GenConst gen = make_gen(rcst, pl->pixel_list, pass0, i0);  // bounce 0 generates its own camera rays
+    launches += 1;
     for (int b = 0; b < p.max_bounces; ++b) {
       const bool last = (b == p.max_bounces - 1);
       if (profile) {
@@ -399,8 +425,8 @@ static int render_impl(ptb_scene *s, const ptb_params &p, R *d_sums, cudaStream_
         tev.push_back(a);
         tev.push_back(z);
       }
-      launch_trace<R, 0>(tl, st, sc, w.rays, &ctl->nseg_rays[b], 0u, &ctl->cursor[b], w.mq, &ctl->nseg_mat[b][0],
-                         &ctl->n_rays[b], last ? 0 : 1, d_sums, R(0), R(0), nullptr, nullptr);
+      launch_trace<R, 0>(tl, st, sc, b == 0 ? &gen : nullptr, n, w.rays, &ctl->nseg_rays[b], 0u, &ctl->cursor[b], w.mq,
+                         &ctl->nseg_mat[b][0], &ctl->n_rays[b], last ? 0 : 1, d_sums, R(0), R(0), nullptr, nullptr);
       if (profile) CK(cudaEventRecord(tev.back(), st));
       ++launches;
       if (!last) {
@@ -628,8 +654,9 @@ int ptb_intersect_batch_device(ptb_scene *s, const float *d_o, const float *d_d,
     const long long m = std::min<int64_t>((int64_t)cap, n - first);
     k_pack_rays<float><<<(unsigned)((m + 255) / 256), 256, 0, st>>>(d_o + 3 * first, d_d + 3 * first, m, w.rays);
     CK(cudaMemsetAsync(&pl->ctl->cursor[MAX_BOUNCES], 0, sizeof(unsigned), st));
-    launch_trace<float, 1>(tl, st, sc, w.rays, nullptr, (unsigned)((m + SEG - 1) / SEG), &pl->ctl->cursor[MAX_BOUNCES], w.mq,
-                           nullptr, nullptr, 0, nullptr, t_min, t_max, d_t + first, d_prim + first);
+    launch_trace<float, 1>(tl, st, sc, nullptr, 0u, w.rays, nullptr, (unsigned)((m + SEG - 1) / SEG),
+                           &pl->ctl->cursor[MAX_BOUNCES], w.mq, nullptr, nullptr, 0, nullptr, t_min, t_max, d_t + first,
+                           d_prim + first);
     launches += 2;
   }
   CK(cudaEventRecord(e1, st));
@@ -762,7 +789,7 @@ int ptb_raygen(const ptb_params *p, int64_t first, int64_t n, int32_t *pixel, in
   CK(cudaMalloc((void **)&d_cy, nn * 8));
   if (n > 0) {
     const int pass0 = (int)(first / tmp.npix), i0 = (int)(first % tmp.npix);
-    k_raygen<float><<<(unsigned)((n + 255) / 256), 256>>>(rcst, tmp.pixel_list, pass0, i0, (unsigned)n, q, d_cx, d_cy);
+    k_raygen<float><<<(unsigned)((n + 255) / 256), 256>>>(make_gen(rcst, tmp.pixel_list, pass0, i0), (unsigned)n, q, d_cx, d_cy);
   }
   CK(cudaGetLastError());
   std::vector<Vec4<float>> A(nn), B(nn);
@@ -802,10 +829,10 @@ int ptb_first_hit(ptb_scene *s, const ptb_params *p, float *t_hit, int32_t *prim
   int32_t *d_p = nullptr;
   CK(cudaMalloc((void **)&d_t, n * 4));
   CK(cudaMalloc((void **)&d_p, n * 4));
-  k_raygen<float><<<(unsigned)((n + 255) / 256), 256>>>(rcst, pl->pixel_list, 0, 0, (unsigned)n, w.rays, nullptr, nullptr);
+  k_raygen<float><<<(unsigned)((n + 255) / 256), 256>>>(make_gen(rcst, pl->pixel_list, 0, 0), (unsigned)n, w.rays, nullptr, nullptr);
   CK(cudaMemsetAsync(&pl->ctl->cursor[MAX_BOUNCES], 0, sizeof(unsigned), 0));
-  launch_trace<float, 1>(tl, 0, sc, w.rays, nullptr, (unsigned)((n + SEG - 1) / SEG), &pl->ctl->cursor[MAX_BOUNCES], w.mq,
-                         nullptr, nullptr, 0, nullptr, 0.0f, FLT_MAX, d_t, d_p);
+  launch_trace<float, 1>(tl, 0, sc, nullptr, 0u, w.rays, nullptr, (unsigned)((n + SEG - 1) / SEG),
+                         &pl->ctl->cursor[MAX_BOUNCES], w.mq, nullptr, nullptr, 0, nullptr, 0.0f, FLT_MAX, d_t, d_p);
   CK(cudaGetLastError());
   std::vector<float> ht(n);
   std::vector<int32_t> hp(n);
