@@ -268,6 +268,20 @@ __device__ __forceinline__ double lds_r(unsigned addr, double) {
 }
 __device__ __forceinline__ void sts_r(unsigned addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v)); }
 __device__ __forceinline__ void sts_r(unsigned addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v)); }
+// asynchronous global -> shared copies (LDGSTS), used to keep the next work item of k_shade in flight
+__device__ __forceinline__ void cp_async16(unsigned saddr, const void *g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+template <class R>
+__device__ __forceinline__ void cp_async_vec4(unsigned saddr, const Vec4<R> *g) {
+#pragma unroll
+  for (unsigned k = 0; k < sizeof(Vec4<R>) / 16; ++k) cp_async16(saddr + 16u * k, reinterpret_cast<const char *>(g) + 16 * k);
+}
 // traversal-stack entry = (child ref, t_near): 8 B in float (one 64-bit shared access), 16 B in double
 __device__ __forceinline__ void stk_store(unsigned addr, int ref, float t) {
   asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(ref), "r"(__float_as_int(t)));
@@ -815,34 +829,84 @@ template <class R>
 __global__ void __launch_bounds__(256)
     k_shade(DScene<R> sc, RenderConst rc, int bounce, Queue<R> q0, Queue<R> q1, Queue<R> q2,
             const unsigned *__restrict__ nseg_mat, Queue<R> out, unsigned *__restrict__ nseg_out) {
+  // Software pipeline over the warp's work items (one item = 32 entries of one segment of one material's hit
+  // queue): while item k is shaded, the 48 B entries of item k+1 are already in flight into shared memory
+  // (cp.async, each lane copies and later reads only its own entry) and the segment fill count of item k+2 is
+  // being loaded, so the queue's HBM latency is off the critical path of every iteration.
+  extern __shared__ __align__(16) unsigned char shade_smem[];
   const unsigned lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
   const unsigned c0 = nseg_mat[0], c1 = nseg_mat[1], c2 = nseg_mat[2];
-  const unsigned total = (c0 + c1 + c2) * (SEG / 32);  // work item = 32 entries of one segment of one material
+  const unsigned total = (c0 + c1 + c2) * (SEG / 32);
   const unsigned warps = (gridDim.x * blockDim.x) >> 5;
   const int j = 2 + 2 * bounce;  // take_2d cursor (integrator.ml:20-28): every hit so far took two
   const double alpha_u = rc.alpha[j], alpha_v = rc.alpha[j + 1];
   unsigned ob = NO_SEG, of = 0;  // warp-uniform: this warp's open segment in the output ray queue
-  for (unsigned w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total; w += warps) {
-    int m;
-    unsigned seg = w / (SEG / 32);
-    const unsigned i0 = (w % (SEG / 32)) * 32;
+  constexpr unsigned VB = (unsigned)sizeof(Vec4<R>);
+  // staging slots: [buffer 0/1][A,B,C][thread]
+  const unsigned sbase = (unsigned)__cvta_generic_to_shared(shade_smem);
+  const unsigned slot0 = sbase + threadIdx.x * VB, bufsz = 3u * blockDim.x * VB, arr = blockDim.x * VB;
+  // item -> (material, segment, first entry)
+  auto decode = [&](unsigned w, int &m, unsigned &seg, unsigned &i0) {
+    seg = w / (SEG / 32);
+    i0 = (w % (SEG / 32)) * 32;
     if (seg < c0) m = 0;
     else if (seg < c0 + c1) m = 1, seg -= c0;
     else m = 2, seg -= c0 + c1;
-    const Queue<R> &q = (m == 0) ? q0 : (m == 1 ? q1 : q2);
-    const unsigned nm = (unsigned)q.seg_count[seg];
+  };
+  auto fill_of = [&](unsigned w) -> unsigned {  // valid entries of the item's segment
+    int m;
+    unsigned seg, i0;
+    decode(w, m, seg, i0);
+    const int32_t *sc_ = (m == 0) ? q0.seg_count : (m == 1 ? q1.seg_count : q2.seg_count);
+    return (unsigned)__ldg(sc_ + seg);
+  };
+  auto prefetch = [&](unsigned w, unsigned nm, unsigned buf) {
+    int m;
+    unsigned seg, i0;
+    decode(w, m, seg, i0);
+    if (i0 + lane < nm) {
+      const unsigned i = seg * SEG + i0 + lane;
+      const Vec4<R> *pa = (m == 0) ? q0.A : (m == 1 ? q1.A : q2.A);
+      const Vec4<R> *pb = (m == 0) ? q0.B : (m == 1 ? q1.B : q2.B);
+      const Vec4<R> *pc = (m == 0) ? q0.C : (m == 1 ? q1.C : q2.C);
+      const unsigned dst = slot0 + buf * bufsz;
+      cp_async_vec4<R>(dst, pa + i);
+      cp_async_vec4<R>(dst + arr, pb + i);
+      cp_async_vec4<R>(dst + 2u * arr, pc + i);
+    }
+  };
+  unsigned w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  unsigned nm_cur = 0, nm_next = 0, buf = 0;
+  if (w < total) {
+    nm_cur = fill_of(w);
+    prefetch(w, nm_cur, 0u);
+    if (w + warps < total) nm_next = fill_of(w + warps);
+  }
+  cp_async_commit();
+  for (; w < total; w += warps) {
+    const unsigned w1 = w + warps, w2 = w1 + warps;
+    unsigned nm_next2 = 0;
+    if (w2 < total) nm_next2 = fill_of(w2);         // in flight during this iteration
+    if (w1 < total) prefetch(w1, nm_next, buf ^ 1u);  // in flight during this iteration
+    cp_async_commit();
+    cp_async_wait<1>();  // item w has landed
+    int m;
+    unsigned seg, i0;
+    decode(w, m, seg, i0);
+    const unsigned nm = nm_cur, cbuf = buf;
+    nm_cur = nm_next, nm_next = nm_next2, buf ^= 1u;
     if (i0 >= nm) continue;
    {
-    const unsigned i = seg * SEG + i0 + lane;
     const bool valid = i0 + lane < nm;
     bool alive = false;
     V3<R> no = {R(0), R(0), R(0)}, nd = {R(0), R(0), R(1)}, nattn = {R(0), R(0), R(0)};
     Vec4<R> A = {R(0), R(0), R(0), R(0)}, B = A;
     if (valid) {
-      A = q.A[i];
-      B = q.B[i];
-      const Vec4<R> C = q.C[i];
+      const unsigned src = slot0 + cbuf * bufsz;
+      A = lds_vec4(src, R());
+      B = lds_vec4(src + arr, R());
+      const Vec4<R> C = lds_vec4(src + 2u * arr, R());
       V3<R> p = {A.x, A.y, A.z};
       const V3<R> d = {B.x, B.y, B.z};
       const int offset = r2i(B.w);

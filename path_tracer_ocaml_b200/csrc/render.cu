@@ -408,7 +408,11 @@ static int render_impl(ptb_scene *s, const ptb_params &p, R *d_sums, cudaStream_
   CK(cudaMemsetAsync(ctl, 0, sizeof(Ctl), st));
   CK(cudaEventRecord(e0, st));
   uint64_t launches = 0;
-  const int shade_grid = d->sm_count * 4;
+  const size_t shade_smem = 2 * 3 * 256 * sizeof(Vec4<R>);  // two staging buffers of (A, B, C) per thread
+  CK(cudaFuncSetAttribute(k_shade<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shade_smem));
+  int shade_per_sm = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&shade_per_sm, k_shade<R>, 256, shade_smem));
+  const int shade_grid = d->sm_count * std::max(shade_per_sm, 1);
   for (long long first = 0; first < total; first += (long long)NB) {
     const unsigned n = (unsigned)std::min<long long>((long long)NB, total - first);
     k_batch_ctl<<<1, 128, 0, st>>>(ctl, n, p.max_bounces);
@@ -432,7 +436,7 @@ static int render_impl(ptb_scene *s, const ptb_params &p, R *d_sums, cudaStream_
       if (!last) {
         // a path that is still alive after the last allowed bounce contributes black
         // (integrator.ml:31-32), so the last bounce needs no scatter
-        k_shade<R><<<shade_grid, 256, 0, st>>>(sc, rcst, b, w.mq[0], w.mq[1], w.mq[2], &ctl->nseg_mat[b][0], w.rays,
+        k_shade<R><<<shade_grid, 256, shade_smem, st>>>(sc, rcst, b, w.mq[0], w.mq[1], w.mq[2], &ctl->nseg_mat[b][0], w.rays,
                                                &ctl->nseg_rays[b + 1]);
         ++launches;
       }
