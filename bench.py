@@ -142,10 +142,15 @@ def run_reference(args):
                              "what": "C++ float64 restatement of the OCaml-domains+AVX path (oracle/), not the OCaml binary"},
             "e2e": {"value": value, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    _emit(json.dumps(line))
 
 
 def main():
+    # exactly ONE line on stdout (the JSON): libraries print there too (NCCL's version banner), so everything
+    # else goes to stderr and the JSON line is written to the saved descriptor at the end
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    globals()["_emit"] = lambda line: (real_stdout.write(line + "\n"), real_stdout.flush())
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -238,16 +243,33 @@ def main():
 
     # ---- e2e: through the public API with HOST buffers: scene commit (BVH build + upload of the tables),
     # render, reduce, resolve, and the device->host read of the image, wall clock --------------------------
-    host_img = torch.empty(H, W, 3, dtype=torch.float32).pin_memory() if rank == 0 else None
+    # N=1: the reference-facing C-ABI calls with HOST buffers: ptb_scene_commit (BVH build + host->device
+    # copy of the scene tables) + ptb_render (render, resolve, device->host copy of the float64 image the
+    # reference's Bimage holds).  N>1: commit + sharded render + NCCL reduce + resolve + image to pinned host.
     t = scene.tables()
     h2d = int(t["n_spheres"] * 5 * 8 + t["n_materials"] * 16 + t["n_textures"] * 48 + 256)
+    if world == 1:
+        host_img = torch.empty(H, W, 3, dtype=torch.float64).pin_memory()
+        host_np = host_img.numpy()
+        d2h = int(W * H * 3 * 8)
+        e2e_what = ("ptb_scene_commit (BVH build + table upload) + ptb_render into a pinned host float64 image "
+                    "(render + resolve + device->host copy), wall clock")
+    else:
+        host_img = torch.empty(H, W, 3, dtype=torch.float32).pin_memory() if rank == 0 else None
+        d2h = int(W * H * 3 * 4)
+        e2e_what = ("scene commit (BVH build + table upload) + sharded render + NCCL reduce + resolve + image to "
+                    "pinned host memory, wall clock")
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         scene.commit(local)  # host->device copy of the step's inputs (the scene tables), incl. BVH build
-        step(False)
-        if rank == 0:
-            host_img.copy_(image, non_blocking=False)
+        if world == 1:
+            integ.render(image=host_np)
+            launches[0] += integ.stats.kernel_launches
+        else:
+            step(False)
+            if rank == 0:
+                host_img.copy_(image, non_blocking=False)
     barrier()
     e2e_s = time.perf_counter() - t0
     e2e_val = paths_per_step * args.steps / e2e_s / 1e6
@@ -280,9 +302,15 @@ def main():
     rays_rank0 = timed["rays"]
     trace_tlops = rays_rank0 * a_trace / (max(timed["ms_trace"], 1e-9) * 1e-3) / 1e12  # rank 0's launches
     pipe_tlops = total_rays * a_ray / (total_ms * 1e-3) / 1e12 / world               # per GPU
-    traffic = None
+    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (profiles/): bytes per
+    # ray there x the rays of an average launch here
+    traffic = traffic_note = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "trace_kernel_ncu.json"))).get("dram_bytes_per_launch")
+        tk = json.load(open(os.path.join(ROOT, "profiles", "trace_kernel_ncu.json")))
+        batch = int(os.environ.get("PTB_BATCH", 1 << 26))                        # paths per wavefront batch
+        n_trace_launches = args.steps * MB * -(-(paths_per_step // world) // batch)  # one k_trace per bounce per batch
+        traffic = tk["dram_bytes_per_ray"] * rays_rank0 / n_trace_launches
+        traffic_note = tk.get("note")
     except Exception:
         pass
     hbm_peak = None
@@ -290,7 +318,11 @@ def main():
         hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:
         hbm_peak = 6650.0
-    b_ray = per_ray["box"] * 24 + per_ray["sphere"] * 16 + per_ray["tri"] * 36 + 2 * 96  # SURVEY §8(d) B_ray
+    # algorithmic HBM bytes per ray: the scene is resident in shared memory, so only wavefront state moves —
+    # 48 B entries: rays of bounce >= 1 are written by k_shade and read by k_trace, hits are written by k_trace
+    # and read by k_shade; plus 12 B of film accumulation per path
+    rpp, hpp = per_ray["rays_per_path"], per_ray["hits_per_path"]
+    b_ray = (96.0 * (rpp - 1.0) + 96.0 * hpp + 12.0) / rpp
     line = {
         "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "mrays_per_s": mrays,
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
@@ -302,6 +334,7 @@ def main():
                    "paths_per_step": paths_per_step},
         "roofline": {"bound": "fp32_issue", "kernel": "k_trace<float,0>", "achieved": trace_tlops, "peak": peak.value,
                      "unit": "Tlane-op/s", "frac": trace_tlops / peak.value, "traffic": traffic,
+                     "traffic_note": traffic_note,
                      "algorithmic_lane_ops_per_ray": a_trace,
                      "peak_source": "measured live: ptb_fp32_peak FFMA micro-benchmark on this GPU (MEASURED_PEAKS.json has no FP32 figure)",
                      "per_ray_counts": per_ray, "trace_ms_per_step": timed["ms_trace"] / args.steps,
@@ -313,12 +346,11 @@ def main():
                                       "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)"}},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_val, "unit": "Mpaths/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": int(W * H * 3 * 4), "ms_per_step": 1e3 * e2e_s / args.steps,
-                "what": "scene commit (BVH build + table upload) + render + reduce + resolve + image to pinned host memory"},
+                "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps, "what": e2e_what},
         "gpu_launches": total_launches,
         "clocks": clocks,
     }
-    print(json.dumps(line), flush=True)
+    _emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 

@@ -647,6 +647,9 @@ __global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, 1)
     S.s_nodes = smem_base, S.s_spheres = smem_base + nb, S.s_tris = smem_base + nb + sb;
     S.s_kinds = smem_base + nb + sb + tb;
     __syncthreads();
+    // keep the two hot base addresses in registers (the compiler otherwise re-derives the shared window base
+    // from %cluster_ctaid in every traversal iteration)
+    asm volatile("" : "+r"(S.s_nodes), "+r"(S.s_spheres));
     // the shared-memory sphere records carry r^2 (what the intersection test needs)
     Vec4<R> *ssph = reinterpret_cast<Vec4<R> *>(smem + nb);
     for (unsigned i = tid; i < (unsigned)sc.n_spheres; i += blockDim.x) ssph[i].w *= ssph[i].w;
@@ -802,6 +805,8 @@ __global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, 1)
     // lanes waiting with a leaf sit out node phases, but the primitive tests then run with most of the warp
     // instead of a handful of lanes (warp-loop replay on the host, scripts/bvh_sim: -6 % warp instructions).
     unsigned act = active;
+    int keep_r = keep;
+    asm volatile("" : "+r"(keep_r));  // loop-invariant: keep it in a register instead of re-deriving it
     do {
       if (L.cur >= 0) node_phase<R, SMEM, MODE == 0, sizeof(R) == 8, !SMEM>(L, S, stride, sp_limit);
       const bool at_leaf = L.cur < 0 && L.cur > TRAV_POP;
@@ -811,7 +816,7 @@ __global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, 1)
       }
       if (L.cur == TRAV_POP) pop_phase<R>(L, stride);
       act = __ballot_sync(0xffffffffu, L.cur > TRAV_DONE);
-    } while (__popc(act) >= keep);
+    } while (__popc(act) >= keep_r);
   }
   if (MODE == 0) {
     __syncwarp();

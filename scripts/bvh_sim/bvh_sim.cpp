@@ -59,7 +59,7 @@ static int SORT = 2;   // 0: nearest only, rest in slot order; 1: 3-exchange; 2:
 static int KEEP = 14;  // refill threshold
 static int ONE = 0;  // 1: the leaf phase tests ONE sphere per iteration (multi-sphere leaves stay pending)
 static int LEAF_T = 1; // leaf phase runs when >= LEAF_T lanes hold a leaf, or no lane can do anything else
-static int C_NODE = 93, C_SPH = 36, C_LEAF0 = 12, C_POP0 = 8, C_POPIT = 6, C_LOOP = 14, C_FLUSH = 150, C_REFILL = 110;
+static int C_NODE = 93, C_SPH = 36, C_LEAF0 = 12, C_POP0 = 8, C_POPIT = 6, C_LOOP = 14, C_FLUSH = 90, C_REFILL = 85;
 
 struct Lane {
   Ray r;
