@@ -39,7 +39,8 @@ enum {
   PTB_E_NO_DEVICE = -2, /* no CUDA device / wrong architecture */
   PTB_E_CUDA = -3,      /* a CUDA runtime call failed; message carries cudaGetErrorString */
   PTB_E_STATE = -4,     /* scene not committed, or modified after commit */
-  PTB_E_NOMEM = -5
+  PTB_E_NOMEM = -5,
+  PTB_E_UNSUPPORTED = -6 /* the reference's own "to do" branches (e.g. ascii / big-endian PLY) */
 };
 
 /* ---- scene tables ---------------------------------------------------------------------------- */

@@ -38,6 +38,16 @@ int ptb_scene_load_mesh(ptb_scene *, const float *xyz, int64_t n_vertices, const
 int ptb_mesh_synthetic(int64_t target_faces, uint32_t seed, float *xyz, int64_t cap_vertices,
                        int32_t *faces, int64_t cap_faces, int64_t *nv, int64_t *nf);
 
+/* The subset of PLY that Ply.of_bigstring reads (ply_format/src/ply.ml:340-352: "ply\n" magic, header up to
+ * end_header, binary_little_endian 1.0 only, elements that are all-atomic or exactly one list property), reduced
+ * to what ganesha takes from it (ganesha/bin/main.ml:50-60,182-185): the x,y,z columns of element "vertex"
+ * (float or double, returned as float32 x,y,z interleaved) and the rows of the list property "vertex_indices"
+ * (exactly 3 per row).  On success *xyz and *faces are malloc'ed by the library: release them with ptb_free. */
+int ptb_ply_read_mesh(const char *path, float **xyz, int64_t *n_vertices, int32_t **faces, int64_t *n_faces);
+int ptb_ply_parse_mesh(const void *bytes, int64_t len, float **xyz, int64_t *n_vertices, int32_t **faces,
+                       int64_t *n_faces);
+void ptb_free(void *);
+
 /* table getters (sizes first with NULL buffers) */
 int ptb_scene_counts(const ptb_scene *, int64_t *n_spheres, int64_t *n_vertices,
                      int64_t *n_triangles, int32_t *n_materials, int32_t *n_textures);

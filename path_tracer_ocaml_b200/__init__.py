@@ -7,5 +7,6 @@ reference's own.  There is no CPU fallback: importing works anywhere, but every 
 if the CUDA extension is missing or no GPU is present.
 """
 from .capi import lib, PtbError, Params, Stats, Texture, Material  # noqa: F401
-from .scenes import Scene, shirley_spheres, cornell_box, synthetic_mesh_scene  # noqa: F401
+from .scenes import (Scene, shirley_spheres, cornell_box, synthetic_mesh_scene, synthetic_mesh, mesh_scene,  # noqa: F401
+                     read_ply_mesh, write_ply_mesh, ganesha)
 from .integrator import Integrator, Args  # noqa: F401

@@ -80,6 +80,9 @@ SYMBOLS = {
     "ptb_scene_load_mesh": (C.c_int, [_vp, _fp, C.c_int64, _ip, C.c_int64, C.c_double, _dp]),
     "ptb_mesh_synthetic": (C.c_int, [C.c_int64, C.c_uint32, _fp, C.c_int64, _ip, C.c_int64,
                                      _P(C.c_int64), _P(C.c_int64)]),
+    "ptb_ply_read_mesh": (C.c_int, [C.c_char_p, _P(_fp), _P(C.c_int64), _P(_ip), _P(C.c_int64)]),
+    "ptb_ply_parse_mesh": (C.c_int, [C.c_char_p, C.c_int64, _P(_fp), _P(C.c_int64), _P(_ip), _P(C.c_int64)]),
+    "ptb_free": (None, [_vp]),
     "ptb_scene_counts": (C.c_int, [_vp, _P(C.c_int64), _P(C.c_int64), _P(C.c_int64), _ip, _ip]),
     "ptb_scene_get_spheres": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _ip]),
     "ptb_scene_get_triangles": (C.c_int, [_vp, _dp, _dp, _dp, _ip, _ip, _dp]),

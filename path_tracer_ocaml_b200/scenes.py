@@ -8,6 +8,8 @@ import numpy as np
 from . import capi
 from .capi import check, dptr, fptr, iptr, lib
 
+_fp_t, _ip_t = C.POINTER(C.c_float), C.POINTER(C.c_int32)
+
 
 class Camera:
     """Camera.t (path_tracer/src/camera.ml:46-54): what Camera.ray and Camera.transform read."""
@@ -166,3 +168,52 @@ def mesh_scene(xyz, faces, width, height):
 def synthetic_mesh_scene(target_faces, width, height, seed=0xB200):
     xyz, faces = synthetic_mesh(target_faces, seed)
     return mesh_scene(xyz, faces, width, height)
+
+
+def read_ply_mesh(path_or_bytes):
+    """Ply.of_bigstring subset + ganesha's Mesh.create access pattern (ply_format/src/ply.ml:340-352,
+    ganesha/bin/main.ml:50-60): returns (xyz float32[nv,3], faces int32[nf,3]) of a binary-little-endian PLY."""
+    xyz, faces = _fp_t(), _ip_t()
+    nv, nf = C.c_int64(), C.c_int64()
+    if isinstance(path_or_bytes, (bytes, bytearray)):
+        b = bytes(path_or_bytes)
+        check(lib().ptb_ply_parse_mesh(b, len(b), C.byref(xyz), C.byref(nv), C.byref(faces), C.byref(nf)))
+    else:
+        check(lib().ptb_ply_read_mesh(str(path_or_bytes).encode(), C.byref(xyz), C.byref(nv), C.byref(faces),
+                                      C.byref(nf)))
+    try:
+        v = np.ctypeslib.as_array(xyz, shape=(max(nv.value, 1) * 3,))[:nv.value * 3].copy().reshape(-1, 3)
+        f = np.ctypeslib.as_array(faces, shape=(max(nf.value, 1) * 3,))[:nf.value * 3].copy().reshape(-1, 3)
+    finally:
+        lib().ptb_free(xyz)
+        lib().ptb_free(faces)
+    return v, f
+
+
+def ganesha(ply_path, width, height):
+    """ganesha/bin/main.ml: the PLY mesh + floor + camera, through the restated ply_format subset."""
+    xyz, faces = read_ply_mesh(ply_path)
+    return mesh_scene(xyz, faces, width, height)
+
+
+def write_ply_mesh(path, xyz, faces, vertex_type="float", count_type="uchar", index_type="int", extra_vertex_props=()):
+    """Test/tooling helper: a binary-little-endian PLY with a `vertex` element (x,y,z [+ extra float props]) and
+    a `face` element holding the list property `vertex_indices` — the layout of pbrt-v3-scenes' ganesha.ply."""
+    xyz = np.asarray(xyz).reshape(-1, 3)
+    faces = np.asarray(faces).reshape(-1, 3)
+    vt = {"float": "<f4", "double": "<f8"}[vertex_type]
+    ct = {"uchar": "u1", "uint8": "u1", "int": "<i4", "ushort": "<u2"}[count_type]
+    it = {"int": "<i4", "uint": "<u4", "ushort": "<u2", "short": "<i2"}[index_type]
+    hdr = ["ply", "format binary_little_endian 1.0", "comment written by path_tracer_ocaml_b200",
+           f"element vertex {len(xyz)}"] + [f"property {vertex_type} {n}" for n in ("x", "y", "z")]
+    hdr += [f"property float {n}" for n in extra_vertex_props]
+    hdr += [f"element face {len(faces)}", f"property list {count_type} {index_type} vertex_indices", "end_header"]
+    vrec = np.zeros(len(xyz), dtype=[("p", vt, 3)] + [(n, "<f4") for n in extra_vertex_props])
+    vrec["p"] = xyz
+    frec = np.zeros(len(faces), dtype=[("n", ct), ("i", it, 3)])
+    frec["n"] = 3
+    frec["i"] = faces
+    with open(path, "wb") as f:
+        f.write(("\n".join(hdr) + "\n").encode())
+        f.write(vrec.tobytes())
+        f.write(frec.tobytes())

@@ -1,0 +1,156 @@
+#!/usr/bin/env python
+"""Measures BASELINE.json configs[0..2] (C1 shirley 600x300x32, C2 cornell geometry 1024^2x256x16,
+C3 synthetic ganesha mesh 1920x1080x256) on one GPU: device throughput at the full size plus image parity
+against the oracle at a reduced size of the same scene; and configs[4] (C5), the intersect_batch sweep
+(rays x spheres / triangles, coherent and incoherent rays) against the oracle's AVX2 leaf kernel / scalar
+Moller-Trumbore on the host.  Writes one JSON document to stdout (progress on stderr).
+
+  python scripts/configs_bench.py [--quick] > gpurun_out/configs.json
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import path_tracer_ocaml_b200 as P  # noqa: E402
+from path_tracer_ocaml_b200 import capi  # noqa: E402
+from path_tracer_ocaml_b200.integrator import intersect_batch  # noqa: E402
+import pyoracle as O  # noqa: E402
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def render_config(name, make_scene, W, H, spp, mb, small, reps=3):
+    scene = make_scene(W, H)
+    integ = P.Integrator(scene, W, H, spp, mb, device=0)
+    tree = scene.tree_stats()
+    best = None
+    for _ in range(reps):
+        integ.render(flags=capi.PTB_FLAG_PROFILE)
+        st = integ.stats
+        if best is None or st.ms_device < best["ms_device"]:
+            best = {"ms_device": st.ms_device, "ms_trace": st.ms_trace, "ms_total": st.ms_total, "paths": int(st.paths),
+                    "rays": int(st.rays)}
+    out = {"config": name, "W": W, "H": H, "spp": spp, "max_bounces": mb, "tree": tree, "commit_ms": scene.commit_ms,
+           "mpaths_per_s": best["paths"] / best["ms_device"] / 1e3, "mrays_per_s": best["rays"] / best["ms_device"] / 1e3,
+           "rays_per_path": best["rays"] / best["paths"], **best}
+    # parity at a reduced size of the SAME scene against the oracle (float64 CPU restatement)
+    w, h, s = small
+    sc2 = make_scene(w, h)
+    i2 = P.Integrator(sc2, w, h, s, mb, device=0)
+    img = i2.render()
+    t0 = time.perf_counter()
+    ref, cn = O.OracleScene(sc2.tables()).render(i2.params, n_threads=os.cpu_count())
+    dt = time.perf_counter() - t0
+    d = img - ref
+    out["parity"] = {"W": w, "H": h, "spp": s, "rmse": float(np.sqrt(np.mean(d * d))),
+                     "within_tol": float(np.mean(np.abs(d) <= 0.02 * np.abs(ref) + 1 / 255)),
+                     "bias": float(np.abs(d.mean((0, 1))).max()), "rays_device": int(i2.stats.rays), "rays_oracle": int(cn.rays),
+                     "oracle_mpaths_per_s": cn.paths / dt / 1e6, "oracle_threads": os.cpu_count()}
+    log(json.dumps(out))
+    return out
+
+
+def rays_for(rng, n, lo, hi, coherent):
+    if coherent:  # origins on a sphere of radius 3x the scene extent, aimed at points in the scene box
+        c, ext = 0.5 * (lo + hi), 0.5 * float(np.max(hi - lo))
+        v = rng.normal(size=(n, 3))
+        v /= np.linalg.norm(v, axis=1, keepdims=True)
+        o = c + 3.0 * ext * v[0] + 0.05 * ext * rng.normal(size=(n, 3))  # one viewpoint, jittered
+        tgt = rng.uniform(lo, hi, size=(n, 3))
+        d = tgt - o
+    else:
+        o = rng.uniform(lo, hi, size=(n, 3))
+        d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    return np.ascontiguousarray(o, dtype=np.float32), np.ascontiguousarray(d, dtype=np.float32)
+
+
+def sweep(quick):
+    """C5: rays N x primitives M.  Spheres: uniform centres in [-10,10]^3, r in U[0.05,0.5]; triangles: seeded
+    soup of the same extent (edge ~0.3).  Seeds fixed (0xB200)."""
+    rng = np.random.default_rng(0xB200)
+    res = []
+    n_list = [1 << 20, 1 << 24] if quick else [1 << 20, 1 << 22, 1 << 24, 1 << 26]
+    scenes = [("spheres", m) for m in (4, 16, 64, 256, 1024, 4096)] + [("triangles", t) for t in
+                                                                      ((10_000, 100_000) if quick else (10_000, 100_000, 1_000_000))]
+    lo, hi = np.full(3, -10.0), np.full(3, 10.0)
+    for kind, m in scenes:
+        s = P.Scene()
+        s.set_textures([capi.Texture(kind=capi.PTB_TEX_SOLID, rgb=(0.5, 0.5, 0.5))])
+        s.set_materials([capi.Material(kind=capi.PTB_MAT_LAMBERTIAN, texture=0, index=1.0)])
+        if kind == "spheres":
+            c = rng.uniform(-10, 10, size=(m, 3))
+            s.set_spheres(c[:, 0], c[:, 1], c[:, 2], rng.uniform(0.05, 0.5, size=m))
+        else:
+            a = rng.uniform(-10, 10, size=(m, 3))
+            v = np.concatenate([a, a + rng.normal(scale=0.3, size=(m, 3)), a + rng.normal(scale=0.3, size=(m, 3))])
+            idx = np.stack([np.arange(m), np.arange(m) + m, np.arange(m) + 2 * m], axis=1).astype(np.int32)
+            s.set_triangles(v[:, 0], v[:, 1], v[:, 2], idx)
+        s.set_background(capi.PTB_BG_CONSTANT, (1.0, 1.0, 1.0))
+        t0 = time.perf_counter()
+        s.commit(0)
+        commit_ms = (time.perf_counter() - t0) * 1e3
+        osc = O.OracleScene(s.tables())
+        for coherent in (True, False):
+            for n in n_list:
+                o, d = rays_for(rng, n, lo, hi, coherent)
+                best = None
+                for _ in range(3):
+                    st = capi.Stats()
+                    t, p = intersect_batch(s, o, d, 0.0, 3.0e38, stats=st)
+                    if best is None or st.ms_device < best[0]:
+                        best = (st.ms_device, st.ms_total)
+                row = {"prims": kind, "m": m, "rays": n, "coherent": coherent, "commit_ms": commit_ms,
+                       "gpu_mrays_per_s_device": n / best[0] / 1e3, "gpu_mrays_per_s_host_buffers": n / best[1] / 1e3,
+                       "hit_fraction": float(np.mean(p >= 0))}
+                # CPU side on a bounded sample: the oracle's reference-faithful tree + leaf kernels
+                ns = min(n, 1 << 18)
+                t0 = time.perf_counter()
+                t_ref, p_ref, _ = osc.intersect_batch(o[:ns], d[:ns], 0.0, 3.0e38, n_threads=os.cpu_count())
+                dt = time.perf_counter() - t0
+                row["cpu_mrays_per_s"] = ns / dt / 1e6
+                row["cpu_sample_rays"] = ns
+                row["cpu_threads"] = os.cpu_count()
+                row["prim_agreement"] = float(np.mean(p[:ns] == p_ref))
+                hit = (p[:ns] == p_ref) & (p_ref >= 0)
+                row["t_rel_err_p99"] = float(np.quantile(np.abs(t[:ns][hit] - t_ref[hit]) / t_ref[hit], 0.99)) if hit.any() else 0.0
+                log(json.dumps(row))
+                res.append(row)
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--skip-sweep", action="store_true")
+    ap.add_argument("--mesh-faces", type=int, default=1_000_000)
+    a = ap.parse_args()
+    if P.lib().ptb_device_count() == 0:
+        raise SystemExit("configs_bench.py: no CUDA device; libptb200 has no CPU path")
+    doc = {"configs": [], "sweep": []}
+    white = ("constant", (1.0, 1.0, 1.0), None)
+    doc["configs"].append(render_config("C1 shirley_spheres 600x300 32spp 8b", lambda w, h: P.shirley_spheres(w, h), 600, 300, 32, 8,
+                                        (600, 300, 32)))
+    doc["configs"].append(render_config("C2 cornell geometry 1024x1024 256spp 16b, constant white background (SURVEY D1)",
+                                        lambda w, h: P.cornell_box(w, h, white), 1024, 1024, 64 if a.quick else 256, 16,
+                                        (256, 256, 16)))
+    nf = 100_000 if a.quick else a.mesh_faces
+    doc["configs"].append(render_config(f"C3 synthetic ganesha mesh ({nf} faces) 1920x1080 256spp 8b",
+                                        lambda w, h: P.synthetic_mesh_scene(nf, w, h), 1920, 1080, 32 if a.quick else 256, 8,
+                                        (320, 180, 16)))
+    if not a.skip_sweep:
+        doc["sweep"] = sweep(a.quick)
+    print(json.dumps(doc))
+
+
+if __name__ == "__main__":
+    main()
