@@ -704,21 +704,36 @@ __global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, 1)
             kind = S.kind(L.best, sc.n_spheres);
           }
         }
-        // per-material segmented queues: no global atomic unless a segment fills up
-        unsigned sb0 = (unsigned)lds_i32(ws + (WS_SEG + 0u) * 4u), sf0 = (unsigned)lds_i32(ws + (WS_SEG + 1u) * 4u);
-        unsigned sb1 = (unsigned)lds_i32(ws + (WS_SEG + 2u) * 4u), sf1 = (unsigned)lds_i32(ws + (WS_SEG + 3u) * 4u);
-        unsigned sb2 = (unsigned)lds_i32(ws + (WS_SEG + 4u) * 4u), sf2 = (unsigned)lds_i32(ws + (WS_SEG + 5u) * 4u);
-        __syncwarp();
-        const unsigned d0 = seg_append(kind == 0, sb0, sf0, &nseg_mat[0], q0.seg_count, lane, lt_mask);
-        const unsigned d1 = seg_append(kind == 1, sb1, sf1, &nseg_mat[1], q1.seg_count, lane, lt_mask);
-        const unsigned d2 = seg_append(kind == 2, sb2, sf2, &nseg_mat[2], q2.seg_count, lane, lt_mask);
-        if (lane == 0) {
-          sts_i32(ws + (WS_SEG + 0u) * 4u, (int)sb0), sts_i32(ws + (WS_SEG + 1u) * 4u, (int)sf0);
-          sts_i32(ws + (WS_SEG + 2u) * 4u, (int)sb1), sts_i32(ws + (WS_SEG + 3u) * 4u, (int)sf1);
-          sts_i32(ws + (WS_SEG + 4u) * 4u, (int)sb2), sts_i32(ws + (WS_SEG + 5u) * 4u, (int)sf2);
+        // per-material segmented queues: no global atomic unless a segment fills up.  Lane k (k < 3) keeps the
+        // books of material kind k (its open segment in the warp record); every lane then fetches the numbers
+        // of ITS kind with three shuffles.
+        const unsigned m0 = __ballot_sync(0xffffffffu, kind == 0), m1 = __ballot_sync(0xffffffffu, kind == 1),
+                       m2 = __ballot_sync(0xffffffffu, kind == 2);
+        unsigned old_base = 0, old_fill = 0, new_base = 0;
+        if (lane < 3u && (m0 | m1 | m2) != 0u) {
+          const unsigned mk = lane == 0 ? m0 : (lane == 1 ? m1 : m2);
+          const unsigned cnt = (unsigned)__popc(mk);
+          const unsigned wsk = ws + (WS_SEG + 2u * lane) * 4u;
+          old_base = (unsigned)lds_i32(wsk), old_fill = (unsigned)lds_i32(wsk + 4u);
+          const unsigned room = (old_base == NO_SEG) ? 0u : (unsigned)SEG - old_fill;
+          if (cnt <= room) {
+            sts_i32(wsk + 4u, (int)(old_fill + cnt));
+          } else {  // open a new segment of this kind's queue; the old one is (or becomes) full
+            const Queue<R> &qk = lane == 0 ? q0 : (lane == 1 ? q1 : q2);
+            const unsigned sn = atomicAdd(&nseg_mat[lane], 1u);
+            if (old_base != NO_SEG) qk.seg_count[old_base / SEG] = SEG;
+            new_base = sn * SEG;
+            sts_i32(wsk, (int)new_base), sts_i32(wsk + 4u, (int)(cnt - room));
+          }
         }
+        const unsigned kk = (unsigned)kind & 3u;
+        const unsigned ob = __shfl_sync(0xffffffffu, old_base, kk), of_ = __shfl_sync(0xffffffffu, old_fill, kk),
+                       nb = __shfl_sync(0xffffffffu, new_base, kk);
         if (kind >= 0) {
-          const unsigned dst = kind == 0 ? d0 : (kind == 1 ? d1 : d2);
+          const unsigned mk = kind == 0 ? m0 : (kind == 1 ? m1 : m2);
+          const unsigned rank = (unsigned)__popc(mk & lt_mask);
+          const unsigned room = (ob == NO_SEG) ? 0u : (unsigned)SEG - of_;
+          const unsigned dst = rank < room ? ob + of_ + rank : nb + (rank - room);
           const Queue<R> &q = (kind == 0) ? q0 : (kind == 1 ? q1 : q2);
           q.A[dst] = {r_fma(L.tbest, L.d.x, L.o.x), r_fma(L.tbest, L.d.y, L.o.y), r_fma(L.tbest, L.d.z, L.o.z), pv.w};
           q.B[dst] = {L.d.x, L.d.y, L.d.z, lds_r(pay_r, R())};
@@ -790,6 +805,15 @@ __global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, 1)
         }
         chunk_next += take;
         if (lane == 0 && MODE == 0) sts_i32(ws + WS_FETCHED * 4u, lds_i32(ws + WS_FETCHED * 4u) + (int)take);
+        if (!GEN) {
+          // the entries the NEXT refill will take: start them on their way from HBM into L2 now
+          const unsigned pf = chunk_next + lane;
+          if (pf < chunk_end) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(rays.A + pf));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(rays.B + pf));
+            if (MODE == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(rays.C + pf));
+          }
+        }
       }
       if (lane == 0) sts_i32(ws + WS_NEXT * 4u, (int)chunk_next), sts_i32(ws + WS_END * 4u, (int)chunk_end);
       __syncwarp();
