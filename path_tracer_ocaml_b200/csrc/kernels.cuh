@@ -592,6 +592,8 @@ __global__ void __launch_bounds__(256) k_raygen(GenConst g, unsigned n, Queue<R>
 //   miss -> background * attenuation added into the per-pixel sums (integrator.ml:36)
 //   hit  -> appended to the queue of its material kind, warp-aggregated with __ballot_sync/__popc
 // MODE 0: pipeline.  MODE 1: intersect only (t and caller primitive index per ray).
+// The three per-material hit queues are equal slices of one allocation: queue k starts q_slots entries
+// (q_slots / SEG segment counters) after queue k-1, `q0` is the first.
 //
 // Registers are the scarce resource (1024 threads per SM leave 64 each), so everything the traversal loop
 // does not touch lives in shared memory: the ray's payload (attenuation, pixel, R2 offset) is parked in a
@@ -600,6 +602,7 @@ __global__ void __launch_bounds__(256) k_raygen(GenConst g, unsigned n, Queue<R>
 //
 // Dynamic shared memory: [scene (SMEM)] [stack: stack_cap x threads x ENTRY] [payload: threads x (Vec4 + R)]
 //                        [warp records: warps x WS_WORDS x 4 B]
+constexpr int LEAF_MIN = 8;  // lanes holding a leaf before the warp runs the leaf phase (tuned: 6..12 equal, 1: -4 %)
 constexpr unsigned WS_NEXT = 0, WS_END = 1, WS_FETCHED = 2, WS_SEG = 3 /* base,fill x 3 kinds */, WS_WORDS = 12;
 
 // dynamic shared memory per thread besides the staged scene: stack + payload slot + share of the warp record
@@ -613,7 +616,7 @@ __host__ __device__ constexpr size_t trace_smem_per_thread(int stack_cap) {
 template <class R, int MODE, bool SMEM, bool GEN>
 __global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, 1)
     k_trace(DScene<R> sc, GenConst gen, unsigned gen_n, Queue<R> rays, const unsigned *__restrict__ nseg_ptr, unsigned nseg_imm,
-            unsigned *__restrict__ cursor, int refill_below, int leaf_min, Queue<R> q0, Queue<R> q1, Queue<R> q2,
+            unsigned *__restrict__ cursor, int refill_below, Queue<R> q0, unsigned q_slots,
             unsigned *__restrict__ nseg_mat, unsigned *__restrict__ n_traced, int enqueue_hits, R *__restrict__ sums,
             R tmin_arg, R tmax_arg, R *__restrict__ out_t, int32_t *__restrict__ out_prim) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -719,9 +722,8 @@ __global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, 1)
           if (cnt <= room) {
             sts_i32(wsk + 4u, (int)(old_fill + cnt));
           } else {  // open a new segment of this kind's queue; the old one is (or becomes) full
-            const Queue<R> &qk = lane == 0 ? q0 : (lane == 1 ? q1 : q2);
             const unsigned sn = atomicAdd(&nseg_mat[lane], 1u);
-            if (old_base != NO_SEG) qk.seg_count[old_base / SEG] = SEG;
+            if (old_base != NO_SEG) q0.seg_count[lane * (q_slots / SEG) + old_base / SEG] = SEG;
             new_base = sn * SEG;
             sts_i32(wsk, (int)new_base), sts_i32(wsk + 4u, (int)(cnt - room));
           }
@@ -734,10 +736,10 @@ __global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, 1)
           const unsigned rank = (unsigned)__popc(mk & lt_mask);
           const unsigned room = (ob == NO_SEG) ? 0u : (unsigned)SEG - of_;
           const unsigned dst = rank < room ? ob + of_ + rank : nb + (rank - room);
-          const Queue<R> &q = (kind == 0) ? q0 : (kind == 1 ? q1 : q2);
-          q.A[dst] = {r_fma(L.tbest, L.d.x, L.o.x), r_fma(L.tbest, L.d.y, L.o.y), r_fma(L.tbest, L.d.z, L.o.z), pv.w};
-          q.B[dst] = {L.d.x, L.d.y, L.d.z, lds_r(pay_r, R())};
-          q.C[dst] = {pv.x, pv.y, pv.z, i2r(L.best, R())};
+          const unsigned e = (unsigned)kind * q_slots + dst;  // entry in the joint allocation
+          q0.A[e] = {r_fma(L.tbest, L.d.x, L.o.x), r_fma(L.tbest, L.d.y, L.o.y), r_fma(L.tbest, L.d.z, L.o.z), pv.w};
+          q0.B[e] = {L.d.x, L.d.y, L.d.z, lds_r(pay_r, R())};
+          q0.C[e] = {pv.x, pv.y, pv.z, i2r(L.best, R())};
         }
         __syncwarp();
       }
@@ -825,7 +827,7 @@ __global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, 1)
     }
     // ---------------- traverse until too few lanes are left -------------------------------------
     const int keep = more ? refill_below : 1;
-    // The leaf phase is POSTPONED until at least `leaf_min` lanes hold a leaf (or every traversing lane does):
+    // The leaf phase is POSTPONED until at least LEAF_MIN lanes hold a leaf (or every traversing lane does):
     // lanes waiting with a leaf sit out node phases, but the primitive tests then run with most of the warp
     // instead of a handful of lanes (warp-loop replay on the host, scripts/bvh_sim: -6 % warp instructions).
     unsigned act = active;
@@ -833,9 +835,9 @@ __global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, 1)
     asm volatile("" : "+r"(keep_r));  // loop-invariant: keep it in a register instead of re-deriving it
     do {
       if (L.cur >= 0) node_phase<R, SMEM, MODE == 0, sizeof(R) == 8, !SMEM>(L, S, stride, sp_limit);
-      const bool at_leaf = L.cur < 0 && L.cur > TRAV_POP;
+      const bool at_leaf = (unsigned)(L.cur - (TRAV_POP + 1)) < (unsigned)(0 - (TRAV_POP + 1));  // TRAV_POP < cur < 0
       const unsigned lm = __ballot_sync(0xffffffffu, at_leaf);
-      if (lm != 0u && (__popc(lm) >= leaf_min || lm == act)) {
+      if (__popc(lm) >= LEAF_MIN || lm == act) {  // (lm == 0 never equals act inside the loop)
         if (at_leaf) leaf_phase<R, SMEM, MODE == 0>(L, S);
       }
       if (L.cur == TRAV_POP) pop_phase<R>(L, stride);
@@ -844,9 +846,10 @@ __global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, 1)
   }
   if (MODE == 0) {
     __syncwarp();
+    const unsigned q_segs = q_slots / SEG;
     seg_close((unsigned)lds_i32(ws + (WS_SEG + 0u) * 4u), (unsigned)lds_i32(ws + (WS_SEG + 1u) * 4u), q0.seg_count, lane);
-    seg_close((unsigned)lds_i32(ws + (WS_SEG + 2u) * 4u), (unsigned)lds_i32(ws + (WS_SEG + 3u) * 4u), q1.seg_count, lane);
-    seg_close((unsigned)lds_i32(ws + (WS_SEG + 4u) * 4u), (unsigned)lds_i32(ws + (WS_SEG + 5u) * 4u), q2.seg_count, lane);
+    seg_close((unsigned)lds_i32(ws + (WS_SEG + 2u) * 4u), (unsigned)lds_i32(ws + (WS_SEG + 3u) * 4u), q0.seg_count + q_segs, lane);
+    seg_close((unsigned)lds_i32(ws + (WS_SEG + 4u) * 4u), (unsigned)lds_i32(ws + (WS_SEG + 5u) * 4u), q0.seg_count + 2u * q_segs, lane);
     const unsigned fetched = (unsigned)lds_i32(ws + WS_FETCHED * 4u);
     if (lane == 0 && fetched) atomicAdd(n_traced, fetched);
   }
@@ -856,7 +859,7 @@ __global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, 1)
 // material switch below is warp-uniform.
 template <class R>
 __global__ void __launch_bounds__(256)
-    k_shade(DScene<R> sc, RenderConst rc, int bounce, Queue<R> q0, Queue<R> q1, Queue<R> q2,
+    k_shade(DScene<R> sc, RenderConst rc, int bounce, Queue<R> q0, unsigned q_slots,
             const unsigned *__restrict__ nseg_mat, Queue<R> out, unsigned *__restrict__ nseg_out) {
   // Software pipeline over the warp's work items (one item = 32 entries of one segment of one material's hit
   // queue): while item k is shaded, the 48 B entries of item k+1 are already in flight into shared memory
@@ -887,22 +890,18 @@ __global__ void __launch_bounds__(256)
     int m;
     unsigned seg, i0;
     decode(w, m, seg, i0);
-    const int32_t *sc_ = (m == 0) ? q0.seg_count : (m == 1 ? q1.seg_count : q2.seg_count);
-    return (unsigned)__ldg(sc_ + seg);
+    return (unsigned)__ldg(q0.seg_count + (unsigned)m * (q_slots / SEG) + seg);
   };
   auto prefetch = [&](unsigned w, unsigned nm, unsigned buf) {
     int m;
     unsigned seg, i0;
     decode(w, m, seg, i0);
     if (i0 + lane < nm) {
-      const unsigned i = seg * SEG + i0 + lane;
-      const Vec4<R> *pa = (m == 0) ? q0.A : (m == 1 ? q1.A : q2.A);
-      const Vec4<R> *pb = (m == 0) ? q0.B : (m == 1 ? q1.B : q2.B);
-      const Vec4<R> *pc = (m == 0) ? q0.C : (m == 1 ? q1.C : q2.C);
+      const unsigned i = (unsigned)m * q_slots + seg * SEG + i0 + lane;  // entry in the joint allocation
       const unsigned dst = slot0 + buf * bufsz;
-      cp_async_vec4<R>(dst, pa + i);
-      cp_async_vec4<R>(dst + arr, pb + i);
-      cp_async_vec4<R>(dst + 2u * arr, pc + i);
+      cp_async_vec4<R>(dst, q0.A + i);
+      cp_async_vec4<R>(dst + arr, q0.B + i);
+      cp_async_vec4<R>(dst + 2u * arr, q0.C + i);
     }
   };
   unsigned w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;

@@ -34,8 +34,9 @@ constexpr size_t MAX_PRODUCER_WARPS = 16384;
 template <class R>
 struct Work {
   Queue<R> rays{nullptr, nullptr, nullptr, nullptr};
-  Queue<R> mq[NUM_MAT_KINDS]{};
-  size_t cap = 0;  // rays per batch the queues were sized for
+  Queue<R> mq{nullptr, nullptr, nullptr, nullptr};  // the NUM_MAT_KINDS hit queues: equal slices of one allocation
+  size_t slots = 0;                                   // entries per queue (a multiple of SEG)
+  size_t cap = 0;                                     // rays per batch the queues were sized for
 };
 
 // Per-device work buffers (wavefront queues, control block, pixel list).  They belong to the device,
@@ -90,8 +91,8 @@ static void free_queue(Queue<R> &q) {
 template <class R>
 static void free_work(Work<R> &w) {
   free_queue(w.rays);
-  for (auto &q : w.mq) free_queue(q);
-  w.cap = 0;
+  free_queue(w.mq);
+  w.cap = 0, w.slots = 0;
 }
 void destroy_device_state(DeviceState *d) {
   if (!d) return;
@@ -199,18 +200,17 @@ static int ensure_work(DevicePool *d, size_t cap) {
   if (w.cap >= cap) return PTB_OK;
   free_work(w);
   const size_t segs = (cap + SEG - 1) / SEG + MAX_PRODUCER_WARPS, slots = segs * SEG;
-  auto alloc_q = [&](Queue<R> &q) -> int {
-    CK(cudaMalloc((void **)&q.A, slots * sizeof(Vec4<R>)));
-    CK(cudaMalloc((void **)&q.B, slots * sizeof(Vec4<R>)));
-    CK(cudaMalloc((void **)&q.C, slots * sizeof(Vec4<R>)));
-    CK(cudaMalloc((void **)&q.seg_count, segs * sizeof(int32_t)));
+  auto alloc_q = [&](Queue<R> &q, size_t n) -> int {
+    CK(cudaMalloc((void **)&q.A, n * slots * sizeof(Vec4<R>)));
+    CK(cudaMalloc((void **)&q.B, n * slots * sizeof(Vec4<R>)));
+    CK(cudaMalloc((void **)&q.C, n * slots * sizeof(Vec4<R>)));
+    CK(cudaMalloc((void **)&q.seg_count, n * segs * sizeof(int32_t)));
     return PTB_OK;
   };
   int rc;
-  if ((rc = alloc_q(w.rays))) return rc;
-  for (auto &q : w.mq)
-    if ((rc = alloc_q(q))) return rc;
-  w.cap = cap;
+  if ((rc = alloc_q(w.rays, 1))) return rc;
+  if ((rc = alloc_q(w.mq, NUM_MAT_KINDS))) return rc;
+  w.cap = cap, w.slots = slots;
   return PTB_OK;
 }
 
@@ -302,6 +302,7 @@ static int trace_config(DeviceState *d, const DScene<R> &sc, size_t scene_bytes,
   tl->scene_smem = sc.scene_in_smem != 0;
   if (tl->scene_smem) {
     tl->block = sizeof(R) == 8 ? 512 : 1024;  // = the kernel's __launch_bounds__
+    if (const char *e = std::getenv("PTB_TRACE_BLOCK")) tl->block = std::min(tl->block, std::max(128, std::atoi(e) / 32 * 32));
     while (tl->block > 128 && scene_bytes + per_thread * tl->block > d->smem_optin) tl->block -= 128;
     tl->smem = scene_bytes + per_thread * tl->block;
     if (tl->smem > d->smem_optin) return fail(PTB_E_NOMEM, "trace: scene + stack do not fit shared memory");
@@ -326,14 +327,6 @@ static int trace_config(DeviceState *d, const DScene<R> &sc, size_t scene_bytes,
   }
   return PTB_OK;
 }
-static int leaf_min() {
-  static int v = -1;
-  if (v < 0) {
-    v = 8;
-    if (const char *e = std::getenv("PTB_LEAFMIN")) v = std::min(32, std::max(1, std::atoi(e)));
-  }
-  return v;
-}
 static int refill_below() {
   static int v = -1;
   if (v < 0) {
@@ -345,15 +338,15 @@ static int refill_below() {
 // gen != nullptr: bounce 0, the kernel generates the camera rays [0, gen_n) of the batch itself
 template <class R, int MODE>
 static void launch_trace(const TraceLaunch &tl, cudaStream_t st, const DScene<R> &sc, const GenConst *gen, unsigned gen_n,
-                         Queue<R> rays, const unsigned *nseg_ptr, unsigned nseg_imm, unsigned *cursor, Queue<R> *mq,
-                         unsigned *nseg_mat, unsigned *n_traced, int enqueue_hits, R *sums, R tmin, R tmax, R *out_t,
+                         Queue<R> rays, const unsigned *nseg_ptr, unsigned nseg_imm, unsigned *cursor, Queue<R> mq,
+                         unsigned mq_slots, unsigned *nseg_mat, unsigned *n_traced, int enqueue_hits, R *sums, R tmin, R tmax, R *out_t,
                          int32_t *out_prim) {
   GenConst g;
   std::memset(&g, 0, sizeof g);
   if (gen) g = *gen;
 #define PTB_LAUNCH(SM, GN)                                                                                             \
   k_trace<R, MODE, SM, GN><<<tl.grid, tl.block, tl.smem, st>>>(sc, g, gen_n, rays, nseg_ptr, nseg_imm, cursor,        \
-                                                               refill_below(), leaf_min(), mq[0], mq[1], mq[2], nseg_mat, \
+                                                               refill_below(), mq, mq_slots, nseg_mat,                    \
                                                                n_traced, enqueue_hits, sums, tmin, tmax, out_t, out_prim)
   if (MODE == 0 && gen) {
     if (tl.scene_smem)
@@ -430,13 +423,13 @@ static int render_impl(ptb_scene *s, const ptb_params &p, R *d_sums, cudaStream_
         tev.push_back(z);
       }
       launch_trace<R, 0>(tl, st, sc, b == 0 ? &gen : nullptr, n, w.rays, &ctl->nseg_rays[b], 0u, &ctl->cursor[b], w.mq,
-                         &ctl->nseg_mat[b][0], &ctl->n_rays[b], last ? 0 : 1, d_sums, R(0), R(0), nullptr, nullptr);
+                         (unsigned)w.slots, &ctl->nseg_mat[b][0], &ctl->n_rays[b], last ? 0 : 1, d_sums, R(0), R(0), nullptr, nullptr);
       if (profile) CK(cudaEventRecord(tev.back(), st));
       ++launches;
       if (!last) {
         // a path that is still alive after the last allowed bounce contributes black
         // (integrator.ml:31-32), so the last bounce needs no scatter
-        k_shade<R><<<shade_grid, 256, shade_smem, st>>>(sc, rcst, b, w.mq[0], w.mq[1], w.mq[2], &ctl->nseg_mat[b][0], w.rays,
+        k_shade<R><<<shade_grid, 256, shade_smem, st>>>(sc, rcst, b, w.mq, (unsigned)w.slots, &ctl->nseg_mat[b][0], w.rays,
                                                &ctl->nseg_rays[b + 1]);
         ++launches;
       }
@@ -659,7 +652,7 @@ int ptb_intersect_batch_device(ptb_scene *s, const float *d_o, const float *d_d,
     k_pack_rays<float><<<(unsigned)((m + 255) / 256), 256, 0, st>>>(d_o + 3 * first, d_d + 3 * first, m, w.rays);
     CK(cudaMemsetAsync(&pl->ctl->cursor[MAX_BOUNCES], 0, sizeof(unsigned), st));
     launch_trace<float, 1>(tl, st, sc, nullptr, 0u, w.rays, nullptr, (unsigned)((m + SEG - 1) / SEG),
-                           &pl->ctl->cursor[MAX_BOUNCES], w.mq, nullptr, nullptr, 0, nullptr, t_min, t_max, d_t + first,
+                           &pl->ctl->cursor[MAX_BOUNCES], w.mq, (unsigned)w.slots, nullptr, nullptr, 0, nullptr, t_min, t_max, d_t + first,
                            d_prim + first);
     launches += 2;
   }
@@ -836,7 +829,7 @@ int ptb_first_hit(ptb_scene *s, const ptb_params *p, float *t_hit, int32_t *prim
   k_raygen<float><<<(unsigned)((n + 255) / 256), 256>>>(make_gen(rcst, pl->pixel_list, 0, 0), (unsigned)n, w.rays, nullptr, nullptr);
   CK(cudaMemsetAsync(&pl->ctl->cursor[MAX_BOUNCES], 0, sizeof(unsigned), 0));
   launch_trace<float, 1>(tl, 0, sc, nullptr, 0u, w.rays, nullptr, (unsigned)((n + SEG - 1) / SEG),
-                         &pl->ctl->cursor[MAX_BOUNCES], w.mq, nullptr, nullptr, 0, nullptr, 0.0f, FLT_MAX, d_t, d_p);
+                         &pl->ctl->cursor[MAX_BOUNCES], w.mq, (unsigned)w.slots, nullptr, nullptr, 0, nullptr, 0.0f, FLT_MAX, d_t, d_p);
   CK(cudaGetLastError());
   std::vector<float> ht(n);
   std::vector<int32_t> hp(n);
