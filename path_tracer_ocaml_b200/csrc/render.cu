@@ -45,6 +45,10 @@ struct DevicePool {
   Work<float> wf;
   Work<double> wd;
   Ctl *ctl = nullptr;
+  // ptb_render's device image buffers (per-pixel sums and the resolved image), grown on demand and kept:
+  // allocating and freeing ~300 MB per call costs tens to hundreds of ms of host time on a busy allocator
+  void *sums_buf = nullptr, *img_buf = nullptr;
+  size_t sums_cap = 0, img_cap = 0;
   int32_t *pixel_list = nullptr;
   std::vector<int32_t> pixel_list_host;
   int pl_W = 0, pl_H = 0, pl_rank = -1, pl_world = 0, npix = 0;
@@ -479,10 +483,20 @@ template <class R>
 static int render_host_impl(ptb_scene *s, const ptb_params &p, double *image, ptb_stats *stats) {
   using clk = std::chrono::steady_clock;
   const size_t n3 = (size_t)p.width * p.height * 3;
-  R *d_sums = nullptr;
-  double *d_img = nullptr;
-  CK(cudaMalloc((void **)&d_sums, n3 * sizeof(R)));
-  CK(cudaMalloc((void **)&d_img, n3 * sizeof(double)));
+  DevicePool *pl = s->dev->pool;
+  auto grow = [](void **buf, size_t *cap, size_t bytes) -> int {
+    if (*cap >= bytes) return PTB_OK;
+    cudaFree(*buf);
+    *buf = nullptr, *cap = 0;
+    CK(cudaMalloc(buf, bytes));
+    *cap = bytes;
+    return PTB_OK;
+  };
+  int rc0;
+  if ((rc0 = grow(&pl->sums_buf, &pl->sums_cap, n3 * sizeof(R)))) return rc0;
+  if ((rc0 = grow(&pl->img_buf, &pl->img_cap, n3 * sizeof(double)))) return rc0;
+  R *d_sums = (R *)pl->sums_buf;
+  double *d_img = (double *)pl->img_buf;
   CK(cudaMemsetAsync(d_sums, 0, n3 * sizeof(R), 0));
   int rc = render_impl<R>(s, p, d_sums, 0, stats);
   if (!rc) rc = resolve_impl<R, double>(d_sums, d_img, p.width, p.height, p.samples_per_pixel, p.flags, 0);
@@ -496,8 +510,6 @@ static int render_host_impl(ptb_scene *s, const ptb_params &p, double *image, pt
       stats->kernel_launches += 1;
     }
   }
-  cudaFree(d_sums);
-  cudaFree(d_img);
   return rc;
 }
 
