@@ -49,6 +49,8 @@ struct DevicePool {
   // allocating and freeing ~300 MB per call costs tens to hundreds of ms of host time on a busy allocator
   void *sums_buf = nullptr, *img_buf = nullptr;
   size_t sums_cap = 0, img_cap = 0;
+  void *batch_buf[4] = {nullptr, nullptr, nullptr, nullptr};  // ptb_intersect_batch: origins, directions, t, prim
+  size_t batch_cap[4] = {0, 0, 0, 0};
   int32_t *pixel_list = nullptr;
   std::vector<int32_t> pixel_list_host;
   int pl_W = 0, pl_H = 0, pl_rank = -1, pl_world = 0, npix = 0;
@@ -691,13 +693,18 @@ int ptb_intersect_batch(ptb_scene *s, const float *o, const float *dd, float t_m
   if (rc) return rc;
   if (stats) std::memset(stats, 0, sizeof *stats);
   auto t0 = clk::now();
-  float *d_o = nullptr, *d_d = nullptr, *d_t = nullptr;
-  int32_t *d_p = nullptr;
   const size_t nn = (size_t)std::max<int64_t>(n, 1);
-  CK(cudaMalloc((void **)&d_o, nn * 12));
-  CK(cudaMalloc((void **)&d_d, nn * 12));
-  CK(cudaMalloc((void **)&d_t, nn * 4));
-  CK(cudaMalloc((void **)&d_p, nn * 4));
+  DevicePool *pl = s->dev->pool;  // device staging buffers are kept between calls (grow-only)
+  const size_t want[4] = {nn * 12, nn * 12, nn * 4, nn * 4};
+  for (int k = 0; k < 4; ++k)
+    if (pl->batch_cap[k] < want[k]) {
+      cudaFree(pl->batch_buf[k]);
+      pl->batch_buf[k] = nullptr, pl->batch_cap[k] = 0;
+      CK(cudaMalloc(&pl->batch_buf[k], want[k]));
+      pl->batch_cap[k] = want[k];
+    }
+  float *d_o = (float *)pl->batch_buf[0], *d_d = (float *)pl->batch_buf[1], *d_t = (float *)pl->batch_buf[2];
+  int32_t *d_p = (int32_t *)pl->batch_buf[3];
   auto th = clk::now();
   CK(cudaMemcpy(d_o, o, (size_t)n * 12, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_d, dd, (size_t)n * 12, cudaMemcpyHostToDevice));
@@ -708,7 +715,6 @@ int ptb_intersect_batch(ptb_scene *s, const float *o, const float *dd, float t_m
     CK(cudaMemcpy(t_hit, d_t, (size_t)n * 4, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(prim, d_p, (size_t)n * 4, cudaMemcpyDeviceToHost));
   }
-  cudaFree(d_o), cudaFree(d_d), cudaFree(d_t), cudaFree(d_p);
   if (stats) {
     stats->ms_h2d = ms_h2d;
     stats->ms_d2h = std::chrono::duration<double, std::milli>(clk::now() - td).count();
