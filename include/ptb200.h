@@ -139,7 +139,9 @@ int ptb_scene_tree_stats(const ptb_scene *, int32_t out[8]);
 
 /* Integrator.render (integrator.ml:130-156) with HOST image: `image_rgb` is 3*W*H doubles laid out
  * (y*W + x)*3 + c, row 0 = top — the Bimage f64 rgb layout the reference allocates
- * (render_command.ml:65).  Includes the host<->device copies. */
+ * (render_command.ml:65).  Includes the host<->device copies.  The work buffers (wavefront queues, device
+ * image) belong to the DEVICE and are reused between calls: one render or intersect_batch at a time per
+ * device and process — like the reference, which renders one image per process. */
 int ptb_render(ptb_scene *, const ptb_params *, double *image_rgb, ptb_stats *);
 
 /* Same pipeline, device-resident output: adds this rank's per-pixel sample sums into `d_sums`

@@ -554,6 +554,9 @@ int ptb_scene_commit(ptb_scene *s, int32_t device, double *ms) {
   if (rc) return rc;
   auto t0 = clk::now();
   build_wide_bvh(h, &s->bvh);
+  // the traversal stack holds the tree's exact worst case + the sentinel; refuse trees it cannot hold rather
+  // than dropping pushes on the device
+  if (s->bvh.max_stack + 1 > 97) return fail(PTB_E_INVALID, "commit: tree too deep for the device traversal stack");
   if (s->dev) destroy_device_state(s->dev);
   s->dev = new DeviceState();
   DeviceState *d = s->dev;

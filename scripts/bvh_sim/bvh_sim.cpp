@@ -57,6 +57,9 @@ static bool sphere_hit(int i, const Ray &r, float &tbest) {
 // ---- policy knobs -------------------------------------------------------------------------------
 static int SORT = 2;   // 0: nearest only, rest in slot order; 1: 3-exchange; 2: full sort
 static int KEEP = 14;  // refill threshold
+static int SPEC = 0;   // 1: speculative traversal: a lane parks ONE leaf and keeps traversing
+static int DEFER = 0;  // 1: flush work runs on full warps of parked results (cost C_FLUSH per 32 rays) + C_PARK per event
+static int C_PARK = 25;
 static int ONE = 0;  // 1: the leaf phase tests ONE sphere per iteration (multi-sphere leaves stay pending)
 static int LEAF_T = 1; // leaf phase runs when >= LEAF_T lanes hold a leaf, or no lane can do anything else
 static int C_NODE = 93, C_SPH = 36, C_LEAF0 = 12, C_POP0 = 8, C_POPIT = 6, C_LOOP = 14, C_FLUSH = 90, C_REFILL = 85;
@@ -65,6 +68,7 @@ struct Lane {
   Ray r;
   float idir[3], tbest;
   int best, cur;
+  int pending = 0;  // SPEC: parked leaf code (0 = none)
   std::vector<std::pair<int, float>> stk;
   bool active = false;
 };
@@ -81,6 +85,7 @@ static void init_lane(Lane &L, const Ray &r) {
   L.tbest = 3.4e38f;
   L.best = -1;
   L.cur = 0;
+  L.pending = 0;
   L.stk.clear();
   L.active = true;
 }
@@ -127,6 +132,70 @@ static void warp_iter(Lane *W, Counts &C) {
       for (int k = 3; k >= 1; --k)
         if (tn[order[k]] < INFINITY) L.stk.push_back({ch[order[k]], tn[order[k]]});
     }
+  }
+  if (SPEC) {
+    // park leaves: a lane whose cur is a leaf and whose slot is free parks it and pops on
+    int pend = 0, blocked = 0, other = 0;
+    for (int l = 0; l < 32; ++l) {
+      Lane &L = W[l];
+      if (!L.active) continue;
+      const bool at_leaf = L.cur < 0 && L.cur > POP;
+      if (at_leaf && L.pending == 0) L.pending = L.cur, L.cur = POP;
+    }
+    // pop phase (speculative: tbest does not include the parked leaf)
+    int max_pop = 0;
+    for (int l = 0; l < 32; ++l) {
+      Lane &L = W[l];
+      if (!L.active || L.cur != POP) continue;
+      int it = 0;
+      for (;;) {
+        ++it;
+        if (L.stk.empty()) { L.cur = DONE; break; }
+        auto e = L.stk.back();
+        L.stk.pop_back();
+        C.pop++;
+        if (e.second <= L.tbest) { L.cur = e.first; break; }
+      }
+      any_pop = true;
+      max_pop = std::max(max_pop, it);
+    }
+    for (int l = 0; l < 32; ++l) {
+      Lane &L = W[l];
+      if (!L.active) continue;
+      const bool at_leaf = L.cur < 0 && L.cur > POP;
+      if (L.pending) ++pend;
+      if ((at_leaf && L.pending) || (L.cur == DONE && L.pending)) ++blocked;
+      else if (L.cur != DONE) ++other;
+    }
+    int max_cnt = 0;
+    const bool do_leaf = pend >= LEAF_T || (pend > 0 && other == 0) || blocked >= LEAF_T / 2 + 1;
+    if (do_leaf) {
+      for (int l = 0; l < 32; ++l) {
+        Lane &L = W[l];
+        if (!L.active || !L.pending) continue;
+        any_leaf = true;
+        ++nl_leaf;
+        unsigned code = ~(unsigned)L.pending;
+        int first = code & 0x3FFFFFF, cnt = ((code >> 26) & 15) + 1;
+        max_cnt = std::max(max_cnt, cnt);
+        for (int i = 0; i < cnt; ++i) {
+          C.sph++;
+          if (sphere_hit(B.sphere_order[first + i], L.r, L.tbest)) L.best = first + i;
+        }
+        L.pending = 0;
+      }
+    }
+    for (int l = 0; l < 32; ++l) {
+      Lane &L = W[l];
+      if (L.active && L.cur == DONE && !L.pending) L.active = false;
+    }
+    C.w_iters++;
+    double c = C_LOOP + 6;
+    if (any_node) c += C_NODE, C.w_node++, C.lanes_node += nl_node;
+    if (any_leaf) c += C_LEAF0 + C_SPH * max_cnt, C.w_leaf++, C.w_leaf_sph += max_cnt, C.lanes_leaf += nl_leaf;
+    if (any_pop) c += C_POP0 + C_POPIT * max_pop, C.w_pop++, C.w_popit += max_pop;
+    C.cost += c;
+    return;
   }
   // leaf phase
   int max_cnt = 0;
@@ -202,7 +271,7 @@ static Counts simulate(const std::vector<Ray> &rays) {
     if (more && act < 32) {
       // flush + refill event
       C.w_flush++;
-      C.cost += C_FLUSH + C_REFILL;
+      C.cost += (DEFER ? C_PARK : C_FLUSH) + C_REFILL;
       for (int l = 0; l < 32 && next < rays.size(); ++l)
         if (!W[l].active) init_lane(W[l], rays[next++]), ++act;
     }
@@ -215,10 +284,11 @@ static Counts simulate(const std::vector<Ray> &rays) {
       for (int l = 0; l < 32; ++l) act += W[l].active;
     } while (act >= keep);
     if (!more && act == 0) {
-      C.w_flush++, C.cost += C_FLUSH;
+      C.w_flush++, C.cost += DEFER ? C_PARK : C_FLUSH;
       break;
     }
   }
+  if (DEFER) C.cost += C.rays / 32.0 * C_FLUSH;
   return C;
 }
 
@@ -238,6 +308,8 @@ int main(int argc, char **argv) {
     if (!strncmp(argv[i], "keep=", 5)) KEEP = atoi(argv[i] + 5);
     if (!strncmp(argv[i], "leaft=", 6)) LEAF_T = atoi(argv[i] + 6);
     if (!strncmp(argv[i], "one=", 4)) ONE = atoi(argv[i] + 4);
+    if (!strncmp(argv[i], "defer=", 6)) DEFER = atoi(argv[i] + 6);
+    if (!strncmp(argv[i], "spec=", 5)) SPEC = atoi(argv[i] + 5);
     if (!strncmp(argv[i], "w=", 2)) W = atoi(argv[i] + 2), Hh = W * 9 / 16;
   }
   FILE *f = fopen("/tmp/shirley_scene.bin", "rb");
