@@ -268,6 +268,23 @@ __device__ __forceinline__ double lds_r(unsigned addr, double) {
 }
 __device__ __forceinline__ void sts_r(unsigned addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v)); }
 __device__ __forceinline__ void sts_r(unsigned addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v)); }
+// Packed FP32 (sm_100: one FFMA2 issues two FMAs on a 64-bit register pair).  The traversal kernel is bound by
+// instruction issue, not by the FMA pipe, so halving the slab test's FMA instruction count pays even though
+// the arithmetic rate is the same.
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pack2(float lo, float hi) {
+  f32x2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2_t v, float &lo, float &hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2_t ffma2(f32x2_t a, f32x2_t b, f32x2_t c) {
+  f32x2_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
 // asynchronous global -> shared copies (LDGSTS), used to keep the next work item of k_shade in flight
 __device__ __forceinline__ void cp_async16(unsigned saddr, const void *g) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
@@ -377,6 +394,8 @@ struct Lane {
   int best, cur;
   unsigned sp;             // shared-window byte address of the next free stack entry
   unsigned onx, ony, onz;  // byte offsets of the near x / y / z plane rows inside a node (by direction sign)
+  // float path: (1/d, 1/d) and (-o/d, -o/d) per axis as packed pairs for FFMA2 (idir/oid above are then unused)
+  f32x2_t ix2, iy2, iz2, nox2, noy2, noz2;
 };
 
 template <class R>
@@ -388,6 +407,10 @@ __device__ __forceinline__ void lane_init(Lane<R> &L, V3<R> o, V3<R> d, R tmin, 
   L.o = o, L.d = d;
   L.idir = {safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z)};
   L.oid = {o.x * L.idir.x, o.y * L.idir.y, o.z * L.idir.z};
+  if constexpr (sizeof(R) == 4) {
+    L.ix2 = pack2(L.idir.x, L.idir.x), L.iy2 = pack2(L.idir.y, L.idir.y), L.iz2 = pack2(L.idir.z, L.idir.z);
+    L.nox2 = pack2(-L.oid.x, -L.oid.x), L.noy2 = pack2(-L.oid.y, -L.oid.y), L.noz2 = pack2(-L.oid.z, -L.oid.z);
+  }
   L.a = dot(d, d);
   L.inv_a = r_rcp(L.a);
   L.tmin = tmin, L.tbest = tmax;
@@ -417,18 +440,47 @@ __device__ __forceinline__ void node_phase(Lane<R> &L, const SceneRef<R, SMEM> &
   const R tmin = TMIN0 ? R(0) : L.tmin;
   // float boxes are padded outward on the host (render.cu box_lo/box_hi), which covers the rounding of the
   // plane distances; the unpadded double boxes get a relative slack on the far side instead
-#define PTB_SLAB(k)                                                                                       \
-  R tn##k = r_max(r_max(r_fma(bnx.k, L.idir.x, -L.oid.x), r_fma(bny.k, L.idir.y, -L.oid.y)),              \
-                  r_max(r_fma(bnz.k, L.idir.z, -L.oid.z), tmin));                                         \
-  R tf##k = r_min(r_min(r_fma(bfx.k, L.idir.x, -L.oid.x), r_fma(bfy.k, L.idir.y, -L.oid.y)),              \
-                  r_min(r_fma(bfz.k, L.idir.z, -L.oid.z), L.tbest));                                      \
-  if (sizeof(R) == 8) tf##k *= Lim<R>::far_scale();                                                       \
-  tn##k = (tn##k <= tf##k) ? tn##k : INF;
-  PTB_SLAB(x)
-  PTB_SLAB(y)
-  PTB_SLAB(z)
-  PTB_SLAB(w)
+  R tnx, tny, tnz, tnw;
+  if constexpr (sizeof(R) == 4) {
+    // 12 FFMA2 instead of 24 FFMA: children (x,y) and (z,w) of a row are the register pairs of its LDS.128
+#define PTB_ROW(row, i2, no2, a, b, c, d)                            \
+  float a, b, c, d;                                                  \
+  unpack2(ffma2(pack2(row.x, row.y), L.i2, L.no2), a, b);            \
+  unpack2(ffma2(pack2(row.z, row.w), L.i2, L.no2), c, d);
+    PTB_ROW(bnx, ix2, nox2, nx0, nx1, nx2, nx3)
+    PTB_ROW(bny, iy2, noy2, ny0, ny1, ny2, ny3)
+    PTB_ROW(bnz, iz2, noz2, nz0, nz1, nz2, nz3)
+    PTB_ROW(bfx, ix2, nox2, fx0, fx1, fx2, fx3)
+    PTB_ROW(bfy, iy2, noy2, fy0, fy1, fy2, fy3)
+    PTB_ROW(bfz, iz2, noz2, fz0, fz1, fz2, fz3)
+#undef PTB_ROW
+#define PTB_SLAB(k, i)                                                             \
+  tn##k = fmaxf(fmaxf(nx##i, ny##i), fmaxf(nz##i, tmin));                          \
+  {                                                                                \
+    const float tf_ = fminf(fminf(fx##i, fy##i), fminf(fz##i, L.tbest));           \
+    tn##k = (tn##k <= tf_) ? tn##k : INF;                                          \
+  }
+    PTB_SLAB(x, 0)
+    PTB_SLAB(y, 1)
+    PTB_SLAB(z, 2)
+    PTB_SLAB(w, 3)
 #undef PTB_SLAB
+  } else {
+#define PTB_SLAB(k)                                                                                       \
+  tn##k = r_max(r_max(r_fma(bnx.k, L.idir.x, -L.oid.x), r_fma(bny.k, L.idir.y, -L.oid.y)),                \
+                r_max(r_fma(bnz.k, L.idir.z, -L.oid.z), tmin));                                           \
+  {                                                                                                       \
+    R tf_ = r_min(r_min(r_fma(bfx.k, L.idir.x, -L.oid.x), r_fma(bfy.k, L.idir.y, -L.oid.y)),              \
+                  r_min(r_fma(bfz.k, L.idir.z, -L.oid.z), L.tbest));                                      \
+    tf_ *= Lim<R>::far_scale();                                                                           \
+    tn##k = (tn##k <= tf_) ? tn##k : INF;                                                                 \
+  }
+    PTB_SLAB(x)
+    PTB_SLAB(y)
+    PTB_SLAB(z)
+    PTB_SLAB(w)
+#undef PTB_SLAB
+  }
   int c0 = ch.x, c1 = ch.y, c2 = ch.z, c3 = ch.w;
   R t0 = tnx, t1 = tny, t2 = tnz, t3 = tnw;
   PTB_CSWAP(t0, c0, t1, c1)
