@@ -17,6 +17,10 @@
 #pragma once
 #include <cfloat>
 
+#ifndef PTB_STACK_HOT
+#define PTB_STACK_HOT 12  // shared-memory levels of the hybrid traversal stack (global-memory scenes)
+#endif
+
 
 #include "device_types.cuh"
 
@@ -316,6 +320,37 @@ __device__ __forceinline__ void stk_load(unsigned addr, int &ref, double &t) {
   asm volatile("ld.shared.s32 %0, [%1];" : "=r"(ref) : "r"(addr));
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(t) : "r"(addr + 8u));
 }
+// Where the traversal stack lives.  Shared memory (stack[level][thread], see Lane) when the scene is staged in
+// shared memory too; for big scenes, which run from global memory and want every warp the register file allows,
+// the thread's LOCAL memory (the hardware interleaves it per thread, L1 keeps the few live levels).
+// `sp` is a shared-window byte address in the first case and an entry index in the second.
+constexpr int LOCAL_STACK_CAP = 97;
+template <class R, bool LOCAL>
+struct Stack;
+template <class R>
+struct Stack<R, false> {
+  unsigned stride;
+  __device__ __forceinline__ void store(unsigned sp, int ref, R t) { stk_store(sp, ref, t); }
+  __device__ __forceinline__ void load(unsigned sp, int &ref, R &t) const { stk_load(sp, ref, t); }
+};
+template <class R>
+struct Stack<R, true> {
+  // hybrid: the first HOT levels (where almost all traffic is) sit in shared memory as stack[level][thread], the
+  // rarely reached deep levels in local memory — 64 B of shared memory per thread instead of the tree's worst case
+  static constexpr unsigned stride = 1u;
+  static constexpr unsigned HOT = PTB_STACK_HOT;
+  unsigned s_base, s_stride;  // shared-window address of this thread's level 0, bytes between levels
+  int ref_[LOCAL_STACK_CAP - HOT];
+  R t_[LOCAL_STACK_CAP - HOT];
+  __device__ __forceinline__ void store(unsigned sp, int ref, R t) {
+    if (sp < HOT) stk_store(s_base + sp * s_stride, ref, t);
+    else ref_[sp - HOT] = ref, t_[sp - HOT] = t;
+  }
+  __device__ __forceinline__ void load(unsigned sp, int &ref, R &t) const {
+    if (sp < HOT) stk_load(s_base + sp * s_stride, ref, t);
+    else ref = ref_[sp - HOT], t = t_[sp - HOT];
+  }
+};
 __device__ __forceinline__ Vec4<float> ldg_vec4(const Vec4<float> *p) {
   float4 v = __ldg(reinterpret_cast<const float4 *>(p));
   return {v.x, v.y, v.z, v.w};
@@ -430,7 +465,7 @@ __device__ __forceinline__ void lane_init(Lane<R> &L, V3<R> o, V3<R> d, R tmin, 
 // closest hit is unchanged (measured: +2 % node visits, -10 instructions per node).  CHECK: stack overflow
 // guard (only when the tree's worst case exceeds the capacity).
 template <class R, bool SMEM, bool TMIN0, bool FULLSORT, bool CHECK>
-__device__ __forceinline__ void node_phase(Lane<R> &L, const SceneRef<R, SMEM> &S, unsigned stride, unsigned sp_limit) {
+__device__ __forceinline__ void node_phase(Lane<R> &L, const SceneRef<R, SMEM> &S, Stack<R, !SMEM> &K, unsigned sp_limit) {
   constexpr unsigned ROW = 4u * (unsigned)sizeof(R);
   const Vec4<R> bnx = S.nrow(L.cur, L.onx), bny = S.nrow(L.cur, L.ony), bnz = S.nrow(L.cur, L.onz);
   const Vec4<R> bfx = S.nrow(L.cur, 3u * ROW - L.onx), bfy = S.nrow(L.cur, 5u * ROW - L.ony),
@@ -493,16 +528,16 @@ __device__ __forceinline__ void node_phase(Lane<R> &L, const SceneRef<R, SMEM> &
   L.cur = (t0 < INF) ? c0 : TRAV_POP;
   // (t0 == INF implies t1..t3 == INF: nothing is pushed)
   if (t3 < INF && (!CHECK || L.sp < sp_limit)) {
-    stk_store(L.sp, c3, t3);
-    L.sp += stride;
+    K.store(L.sp, c3, t3);
+    L.sp += K.stride;
   }
   if (t2 < INF && (!CHECK || L.sp < sp_limit)) {
-    stk_store(L.sp, c2, t2);
-    L.sp += stride;
+    K.store(L.sp, c2, t2);
+    L.sp += K.stride;
   }
   if (t1 < INF && (!CHECK || L.sp < sp_limit)) {
-    stk_store(L.sp, c1, t1);
-    L.sp += stride;
+    K.store(L.sp, c1, t1);
+    L.sp += K.stride;
   }
 }
 
@@ -526,12 +561,12 @@ __device__ __forceinline__ void leaf_phase(Lane<R> &L, const SceneRef<R, SMEM> &
 
 // pop, skipping subtrees that start beyond the current best hit; the sentinel (t = -inf) always stops the
 // loop and leaves cur == TRAV_DONE: the ray is finished (lane_init resets sp)
-template <class R>
-__device__ __forceinline__ void pop_phase(Lane<R> &L, unsigned stride) {
+template <class R, bool LOCAL>
+__device__ __forceinline__ void pop_phase(Lane<R> &L, const Stack<R, LOCAL> &K) {
   R t;
   do {
-    L.sp -= stride;
-    stk_load(L.sp, L.cur, t);
+    L.sp -= K.stride;
+    K.load(L.sp, L.cur, t);
   } while (t > L.tbest);
 }
 
@@ -659,14 +694,15 @@ constexpr unsigned WS_NEXT = 0, WS_END = 1, WS_FETCHED = 2, WS_SEG = 3 /* base,f
 
 // dynamic shared memory per thread besides the staged scene: stack + payload slot + share of the warp record
 template <class R>
-__host__ __device__ constexpr size_t trace_smem_per_thread(int stack_cap) {
-  return (size_t)stack_cap * 2u * sizeof(R) + sizeof(Vec4<R>) + sizeof(R) + (WS_WORDS * 4u + 31u) / 32u;
+__host__ __device__ constexpr size_t trace_smem_per_thread(int stack_cap, bool stack_in_smem) {
+  return (size_t)(stack_in_smem ? stack_cap : PTB_STACK_HOT) * 2u * sizeof(R) + sizeof(Vec4<R>) + sizeof(R) +
+         (WS_WORDS * 4u + 31u) / 32u;
 }
 
 // GEN: bounce 0 — the rays are the camera samples [0, gen_n) of the batch, generated in registers
 // (camera_sample) instead of being read from `rays`.
 template <class R, int MODE, bool SMEM, bool GEN>
-__global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, 1)
+__global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, SMEM ? 1 : (sizeof(R) == 8 ? 1 : 3))
     k_trace(DScene<R> sc, GenConst gen, unsigned gen_n, Queue<R> rays, const unsigned *__restrict__ nseg_ptr, unsigned nseg_imm,
             unsigned *__restrict__ cursor, int refill_below, Queue<R> q0, unsigned q_slots,
             unsigned *__restrict__ nseg_mat, unsigned *__restrict__ n_traced, int enqueue_hits, R *__restrict__ sums,
@@ -712,13 +748,24 @@ __global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, 1)
   }
   // traversal stack: stack[level][thread], entry = (ref, t_near); level 0 is the sentinel
   constexpr unsigned ENTRY = 2u * (unsigned)sizeof(R);
-  const unsigned stride = blockDim.x * ENTRY;
-  const unsigned stk0 = smem_base + scene_bytes + (unsigned)tid * ENTRY;
-  stk_store(stk0, TRAV_DONE, -Lim<R>::inf());
-  const unsigned sp0 = stk0 + stride;
-  const unsigned sp_limit = stk0 + (unsigned)sc.stack_cap * stride;  // entries [1, stack_cap) hold pushes
+  Stack<R, !SMEM> K;
+  unsigned sp0, sp_limit, pay_base;
+  if constexpr (SMEM) {
+    K.stride = blockDim.x * ENTRY;
+    const unsigned stk0 = smem_base + scene_bytes + (unsigned)tid * ENTRY;
+    K.store(stk0, TRAV_DONE, -Lim<R>::inf());
+    sp0 = stk0 + K.stride;
+    sp_limit = stk0 + (unsigned)sc.stack_cap * K.stride;  // entries [1, stack_cap) hold pushes
+    pay_base = smem_base + scene_bytes + (unsigned)sc.stack_cap * K.stride;
+  } else {
+    K.s_stride = blockDim.x * ENTRY;
+    K.s_base = smem_base + (unsigned)tid * ENTRY;
+    K.store(0u, TRAV_DONE, -Lim<R>::inf());
+    sp0 = 1u;
+    sp_limit = (unsigned)min(sc.stack_cap, LOCAL_STACK_CAP);
+    pay_base = smem_base + Stack<R, true>::HOT * K.s_stride;
+  }
   // per-thread payload slot and per-warp record
-  const unsigned pay_base = smem_base + scene_bytes + (unsigned)sc.stack_cap * stride;
   const unsigned pay_v = pay_base + (unsigned)tid * (unsigned)sizeof(Vec4<R>);
   const unsigned pay_r = pay_base + blockDim.x * (unsigned)sizeof(Vec4<R>) + (unsigned)tid * (unsigned)sizeof(R);
   const unsigned ws = pay_base + blockDim.x * (unsigned)(sizeof(Vec4<R>) + sizeof(R)) + ((unsigned)tid >> 5) * (WS_WORDS * 4u);
@@ -886,13 +933,13 @@ __global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, 1)
     int keep_r = keep;
     asm volatile("" : "+r"(keep_r));  // loop-invariant: keep it in a register instead of re-deriving it
     do {
-      if (L.cur >= 0) node_phase<R, SMEM, MODE == 0, sizeof(R) == 8, !SMEM>(L, S, stride, sp_limit);
+      if (L.cur >= 0) node_phase<R, SMEM, MODE == 0, sizeof(R) == 8, !SMEM>(L, S, K, sp_limit);
       const bool at_leaf = (unsigned)(L.cur - (TRAV_POP + 1)) < (unsigned)(0 - (TRAV_POP + 1));  // TRAV_POP < cur < 0
       const unsigned lm = __ballot_sync(0xffffffffu, at_leaf);
       if (__popc(lm) >= LEAF_MIN || lm == act) {  // (lm == 0 never equals act inside the loop)
         if (at_leaf) leaf_phase<R, SMEM, MODE == 0>(L, S);
       }
-      if (L.cur == TRAV_POP) pop_phase<R>(L, stride);
+      if (L.cur == TRAV_POP) pop_phase<R, !SMEM>(L, K);
       act = __ballot_sync(0xffffffffu, L.cur > TRAV_DONE);
     } while (__popc(act) >= keep_r);
   }

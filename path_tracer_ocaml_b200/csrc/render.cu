@@ -304,7 +304,7 @@ struct TraceLaunch {
 // blocks at whatever occupancy the stack allows.
 template <class R, int MODE>
 static int trace_config(DeviceState *d, const DScene<R> &sc, size_t scene_bytes, TraceLaunch *tl) {
-  const size_t per_thread = trace_smem_per_thread<R>(sc.stack_cap);  // stack + payload slot + warp record
+  const size_t per_thread = trace_smem_per_thread<R>(sc.stack_cap, sc.scene_in_smem != 0);  // (stack +) payload + warp record
   tl->scene_smem = sc.scene_in_smem != 0;
   if (tl->scene_smem) {
     tl->block = sizeof(R) == 8 ? 512 : 1024;  // = the kernel's __launch_bounds__
