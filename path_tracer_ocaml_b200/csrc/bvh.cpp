@@ -9,11 +9,15 @@
 // homogeneous (the reference's cornell `Shape` sum type, cornell-box/bin/main.ml:93-155, becomes a
 // type bit in the leaf code).  Closest-hit results do not depend on the tree shape.
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <queue>
+#include <thread>
 
 #include "scene.hpp"
 
@@ -51,25 +55,63 @@ static const Tune &tune() {
   return t;
 }
 
+// A range handed to a worker thread: its subtree is built into a private node vector and stitched in afterwards.
+struct SubtreeTask {
+  int node;    // placeholder in the shared node vector
+  int lo, hi;  // primitive range
+  std::vector<BinNode> local;
+};
+
 struct BinaryBuilder {
   std::vector<PrimRef> &prims;
   std::vector<BinNode> &nodes;
   int type;
   int base;  // offset of this type's slot range
+  std::vector<SubtreeTask> *defer = nullptr;  // non-null: ranges of at most `defer_below` primitives become tasks
+  int defer_below = 0;
 
   int build(int lo, int hi) {
-    Box box;
-    box.reset();
-    Box cbox;
-    cbox.reset();
-    for (int i = lo; i < hi; ++i) {
-      box.grow(prims[i].box);
-      for (int a = 0; a < 3; ++a) {
-        cbox.mn[a] = std::min(cbox.mn[a], prims[i].c[a]);
-        cbox.mx[a] = std::max(cbox.mx[a], prims[i].c[a]);
-      }
+    if (defer && hi - lo <= defer_below && hi - lo > 64) {
+      int me = (int)nodes.size();
+      nodes.emplace_back();
+      defer->push_back(SubtreeTask{me, lo, hi, {}});
+      return me;
     }
-    int n = hi - lo;
+    const int n = hi - lo;
+    // big ranges of the (serial) top phase: bounds and bins are reduced over chunks by a few threads
+    static const unsigned hw = std::max(1u, std::thread::hardware_concurrency());  // (a syscall: ask once)
+    const int nchunk = (defer && n >= 65536) ? (int)std::min(hw, 16u) : 1;
+    auto for_chunks = [&](auto &&f) {
+      if (nchunk == 1) {
+        f(lo, hi, 0);
+        return;
+      }
+      std::vector<std::thread> th;
+      for (int c = 1; c < nchunk; ++c)
+        th.emplace_back([&, c] { f(lo + (int)((long long)n * c / nchunk), lo + (int)((long long)n * (c + 1) / nchunk), c); });
+      f(lo, lo + n / nchunk, 0);
+      for (auto &t : th) t.join();
+    };
+    struct Bounds {
+      Box box, cbox;
+    };
+    Bounds pb1;
+    std::vector<Bounds> pbv;
+    if (nchunk > 1) pbv.resize((size_t)nchunk);
+    Bounds *pb = nchunk > 1 ? pbv.data() : &pb1;
+    for_chunks([&](int clo, int chi, int slot) {
+      Bounds &B = pb[slot];
+      B.box.reset(), B.cbox.reset();
+      for (int i = clo; i < chi; ++i) {
+        B.box.grow(prims[i].box);
+        for (int a = 0; a < 3; ++a) {
+          B.cbox.mn[a] = std::min(B.cbox.mn[a], prims[i].c[a]);
+          B.cbox.mx[a] = std::max(B.cbox.mx[a], prims[i].c[a]);
+        }
+      }
+    });
+    Box box = pb[0].box, cbox = pb[0].cbox;
+    for (int c = 1; c < nchunk; ++c) box.grow(pb[c].box), cbox.grow(pb[c].cbox);
     int me = (int)nodes.size();
     nodes.emplace_back();
     nodes[me].box = box;
@@ -80,22 +122,44 @@ struct BinaryBuilder {
       return me;
     };
     if (n <= tune().leaf_max && n <= tune().min_leaf) return make_leaf();
-    // binned SAH over the three axes
+    // binned SAH over the three axes: one pass fills the bins of all three
+    struct Bins {
+      Box bb[3][NBINS];
+      int cnt[3][NBINS];
+    };
+    double kk[3];
+    bool use[3];
+    for (int a = 0; a < 3; ++a) {
+      const double ext = cbox.mx[a] - cbox.mn[a];
+      use[a] = ext > 0.0;
+      kk[a] = use[a] ? NBINS * (1.0 - 1e-9) / ext : 0.0;
+    }
+    Bins bins1;
+    std::vector<Bins> binsv;
+    if (nchunk > 1) binsv.resize((size_t)nchunk);
+    Bins *bins = nchunk > 1 ? binsv.data() : &bins1;
+    for_chunks([&](int clo, int chi, int slot) {
+      Bins &B = bins[slot];
+      for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < NBINS; ++b) B.bb[a][b].reset(), B.cnt[a][b] = 0;
+      for (int i = clo; i < chi; ++i)
+        for (int a = 0; a < 3; ++a) {
+          if (!use[a]) continue;
+          int b = (int)(kk[a] * (prims[i].c[a] - cbox.mn[a]));
+          b = std::min(std::max(b, 0), NBINS - 1);
+          B.bb[a][b].grow(prims[i].box);
+          B.cnt[a][b]++;
+        }
+    });
+    for (int c = 1; c < nchunk; ++c)
+      for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < NBINS; ++b) bins[0].bb[a][b].grow(bins[c].bb[a][b]), bins[0].cnt[a][b] += bins[c].cnt[a][b];
     double best_cost = 1e300;
     int best_axis = -1, best_split = -1;
     for (int a = 0; a < 3; ++a) {
-      double ext = cbox.mx[a] - cbox.mn[a];
-      if (!(ext > 0.0)) continue;
-      double k = NBINS * (1.0 - 1e-9) / ext;
-      Box bb[NBINS];
-      int cnt[NBINS];
-      for (int b = 0; b < NBINS; ++b) bb[b].reset(), cnt[b] = 0;
-      for (int i = lo; i < hi; ++i) {
-        int b = (int)(k * (prims[i].c[a] - cbox.mn[a]));
-        b = std::min(std::max(b, 0), NBINS - 1);
-        bb[b].grow(prims[i].box);
-        cnt[b]++;
-      }
+      if (!use[a]) continue;
+      const Box *bb = bins[0].bb[a];
+      const int *cnt = bins[0].cnt[a];
       double right_area[NBINS];
       int right_cnt[NBINS];
       Box acc;
@@ -151,6 +215,13 @@ struct BinaryBuilder {
 }  // namespace
 
 void build_wide_bvh(const HostScene &s, WideBVH *out) {
+  const bool timing = std::getenv("PTB_BVH_TIMING") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto t_start = now();
+  auto lap = [&](const char *what) {
+    if (timing) std::fprintf(stderr, "[bvh] %-10s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now() - t_start).count());
+    t_start = now();
+  };
   out->nodes.clear();
   out->sphere_order.clear();
   out->tri_order.clear();
@@ -176,15 +247,47 @@ void build_wide_bvh(const HostScene &s, WideBVH *out) {
     for (int a = 0; a < 3; ++a) p.c[a] = 0.5 * (p.box.mn[a] + p.box.mx[a]);
     p.id = (int32_t)i;
   }
+  // Big inputs: the top of the tree is built on this thread down to ranges of about n / (8 x threads) primitives;
+  // those subtrees are independent (disjoint primitive ranges, sorted in place) and are built by a pool of
+  // threads into private node vectors, then appended with their indices shifted.
+  auto build_all = [&](std::vector<PrimRef> &prims, int type) -> int {
+    const int n = (int)prims.size();
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    if (n < 65536 || hw < 2) {
+      BinaryBuilder b{prims, bn, type, 0};
+      return b.build(0, n);
+    }
+    std::vector<SubtreeTask> tasks;
+    BinaryBuilder top{prims, bn, type, 0, &tasks, std::max(4096, n / (int)(8 * hw))};
+    const int root = top.build(0, n);
+    std::atomic<size_t> next{0};
+    auto worker = [&]() {
+      for (size_t i; (i = next.fetch_add(1)) < tasks.size();) {
+        BinaryBuilder b{prims, tasks[i].local, type, 0};
+        b.build(tasks[i].lo, tasks[i].hi);
+      }
+    };
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < std::min<size_t>(hw, tasks.size()); ++t) pool.emplace_back(worker);
+    worker();
+    for (auto &t : pool) t.join();
+    for (SubtreeTask &t : tasks) {
+      // local[0] replaces the placeholder, local[1..] go to the end; child indices move accordingly
+      const int shift = (int)bn.size() - 1;
+      auto fix = [&](BinNode nd) {
+        if (!nd.leaf()) nd.lhs += shift, nd.rhs += shift;
+        return nd;
+      };
+      bn[t.node] = fix(t.local[0]);
+      for (size_t j = 1; j < t.local.size(); ++j) bn.push_back(fix(t.local[j]));
+    }
+    return root;
+  };
+  lap("prims");
   int sroot = -1, troot = -1;
-  if (!sph.empty()) {
-    BinaryBuilder b{sph, bn, 0, 0};
-    sroot = b.build(0, (int)sph.size());
-  }
-  if (!tri.empty()) {
-    BinaryBuilder b{tri, bn, 1, 0};
-    troot = b.build(0, (int)tri.size());
-  }
+  if (!sph.empty()) sroot = build_all(sph, 0);
+  if (!tri.empty()) troot = build_all(tri, 1);
+  lap("binary");
   for (auto &p : sph) out->sphere_order.push_back(p.id);
   for (auto &p : tri) out->tri_order.push_back(p.id);
 
@@ -226,6 +329,7 @@ void build_wide_bvh(const HostScene &s, WideBVH *out) {
     for (int c : ch)
       if (!bn[c].leaf()) q.push({{bn[c].lhs, bn[c].rhs}, cur.depth + 1});
   }
+  lap("collapse");
   // second pass: emit nodes; inner children get indices in the same BFS order
   out->nodes.resize(child_sets.size());
   int next_inner = 1;
@@ -261,6 +365,7 @@ void build_wide_bvh(const HostScene &s, WideBVH *out) {
     need[i] = std::max(m - 1, 0) + deepest;
   }
   out->max_stack = need.empty() ? 1 : std::max(need[0], 1);
+  lap("emit");
 }
 
 }  // namespace ptb
