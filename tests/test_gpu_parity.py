@@ -116,6 +116,14 @@ def test_first_hit_map_mesh():
     _first_hit_check(P.synthetic_mesh_scene(20000, 320, 180), 320, 180, prim_frac=0.995)
 
 
+def test_first_hit_map_big_mesh_threaded_tree_build():
+    # >= 65536 primitives: the host builder hands subtrees to a thread pool (bvh.cpp); same closest hits
+    scene = P.synthetic_mesh_scene(150000, 240, 135)
+    _first_hit_check(scene, 240, 135, prim_frac=0.99)
+    st = scene.tree_stats()
+    assert st["triangles"] >= 140000 and st["max_stack"] + 1 <= 97
+
+
 def _random_rays(rng, n, lo, hi):
     o = rng.uniform(lo, hi, size=(n, 3))
     d = rng.normal(size=(n, 3))
