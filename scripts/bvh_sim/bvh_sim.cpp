@@ -57,6 +57,7 @@ static bool sphere_hit(int i, const Ray &r, float &tbest) {
 // ---- policy knobs -------------------------------------------------------------------------------
 static int SORT = 2;   // 0: nearest only, rest in slot order; 1: 3-exchange; 2: full sort
 static int KEEP = 14;  // refill threshold
+static int OCT = 0;    // 1: k_shade bins outgoing rays by direction octant (8 open segments per producer warp)
 static int SPEC = 0;   // 1: speculative traversal: a lane parks ONE leaf and keeps traversing
 static int DEFER = 0;  // 1: flush work runs on full warps of parked results (cost C_FLUSH per 32 rays) + C_PARK per event
 static int C_PARK = 25;
@@ -310,6 +311,7 @@ int main(int argc, char **argv) {
     if (!strncmp(argv[i], "one=", 4)) ONE = atoi(argv[i] + 4);
     if (!strncmp(argv[i], "defer=", 6)) DEFER = atoi(argv[i] + 6);
     if (!strncmp(argv[i], "spec=", 5)) SPEC = atoi(argv[i] + 5);
+    if (!strncmp(argv[i], "oct=", 4)) OCT = atoi(argv[i] + 4);
     if (!strncmp(argv[i], "w=", 2)) W = atoi(argv[i] + 2), Hh = W * 9 / 16;
   }
   FILE *f = fopen("/tmp/shirley_scene.bin", "rb");
@@ -389,6 +391,23 @@ int main(int argc, char **argv) {
   Counts T;
   printf("bounce  rays   node/ray sph/ray pop/ray | warp: cost/ray  iters/ray*32 lanes@node lanes@leaf sph/leafstep flush/ray*32\n");
   for (int b = 0; b < 8; ++b) {
+    if (OCT && b > 0) {
+      // emulate the producer: NPROD warps take 32-ray items round-robin; each keeps 8 open 128-ray segments
+      const int NPROD = 64;
+      std::vector<std::vector<Ray>> open((size_t)NPROD * 8);
+      std::vector<Ray> out;
+      const std::vector<Ray> &in = per_bounce[b];
+      for (size_t i = 0; i < in.size(); ++i) {
+        const int w = (int)((i / 32) % NPROD);
+        const Ray &r = in[i];
+        const int o = (r.d[0] < 0) | ((r.d[1] < 0) << 1) | ((r.d[2] < 0) << 2);
+        auto &seg = open[(size_t)w * 8 + o];
+        seg.push_back(r);
+        if (seg.size() == 128) out.insert(out.end(), seg.begin(), seg.end()), seg.clear();
+      }
+      for (auto &seg : open) out.insert(out.end(), seg.begin(), seg.end());
+      per_bounce[b] = out;
+    }
     Counts C = simulate(per_bounce[b]);
     printf("%d %8.0f  %6.2f  %6.2f  %6.2f | %8.2f  %6.2f  %5.1f  %5.1f  %5.2f  %5.2f\n", b, C.rays, C.node / C.rays,
            C.sph / C.rays, C.pop / C.rays, C.cost / C.rays, C.w_iters / C.rays * 32, C.lanes_node / std::max(1.0, C.w_node),
