@@ -144,6 +144,15 @@ int ptb_scene_tree_stats(const ptb_scene *, int32_t out[8]);
  * device and process — like the reference, which renders one image per process. */
 int ptb_render(ptb_scene *, const ptb_params *, double *image_rgb, ptb_stats *);
 
+/* Single-process multi-GPU render (BASELINE.json configs[3]): the scene is replicated on devices
+ * 0..n_devices-1 (the tree is built once), device i renders the tiles t = i (mod n_devices) of the reference's tile
+ * list (Tile.split ~max_area:1024, integrator.ml:132-133) on its own host thread, then device 0 adds the other
+ * devices' per-pixel sums straight out of their memory (peer loads over NVLink) and resolves.  Same image layout
+ * as ptb_render; float32 pipeline only.  This is what the CLI twin's --gpus N calls; one process per GPU with an
+ * NCCL reduce (ptb_render_device + ptb_resolve_device) is the other way to shard. */
+int ptb_scene_commit_multi(ptb_scene *, int32_t n_devices, double *ms);
+int ptb_render_multi(ptb_scene *, const ptb_params *, int32_t n_devices, double *image_rgb, ptb_stats *);
+
 /* Same pipeline, device-resident output: adds this rank's per-pixel sample sums into `d_sums`
  * (float32[3*W*H], same layout, device memory on params->device), enqueued on `stream`
  * (a cudaStream_t; NULL = default stream).  The caller zeroes d_sums, reduces it across ranks, and

@@ -59,6 +59,8 @@ SYMBOLS = {
     "ptb_scene_primitive_count": (C.c_int64, [_vp]),
     "ptb_scene_tree_stats": (C.c_int, [_vp, _ip]),
     "ptb_render": (C.c_int, [_vp, _P(Params), _dp, _P(Stats)]),
+    "ptb_scene_commit_multi": (C.c_int, [_vp, C.c_int32, _dp]),
+    "ptb_render_multi": (C.c_int, [_vp, _P(Params), C.c_int32, _dp, _P(Stats)]),
     "ptb_render_device": (C.c_int, [_vp, _P(Params), _vp, _vp, _P(Stats)]),
     "ptb_resolve_device": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp]),
     "ptb_intersect_batch": (C.c_int, [_vp, _fp, _fp, C.c_float, C.c_float, C.c_int64, _fp, _ip, C.c_int32,

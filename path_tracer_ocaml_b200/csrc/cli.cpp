@@ -8,7 +8,7 @@
 //   shirley_spheres --dimension=600,300 --samples-per-pixel=32 --max-ray-bounces=8 [-o out.png] [--no-simd]
 //   cornell_box     -d 1024,1024 --samples-per-pixel=256 --max-ray-bounces=16 [--background white|sky]
 //   ganesha         -d 1920,1080 --samples-per-pixel=256 (--ganesha-ply FILE | --synthetic-faces N)
-//   common: [--no-progress] [--device cuda[:N]] [--f64] [--ppm]
+//   common: [--no-progress] [--device cuda[:N]] [--gpus N] [--f64]   (output *.ppm writes a PPM instead of a PNG)
 //
 // cornell_box and ganesha render through the path integrator here (the reference's own binaries use the
 // progressive photon mapper, which is out of scope: SURVEY.md D1/D2).
@@ -27,7 +27,7 @@
 namespace {
 
 struct Args {  // Render_command.Args.t (render_command.ml:6-14) + what the port adds
-  int width = 0, height = 0, samples_per_pixel = 1, max_bounces = 8, device = 0;
+  int width = 0, height = 0, samples_per_pixel = 1, max_bounces = 8, device = 0, gpus = 1;
   std::string output = "output.png";
   bool no_progress = false, no_simd = false, f64 = false;
   std::string ply, background = "white";
@@ -132,7 +132,8 @@ Args parse(int argc, char **argv, int first) {
       if (v == "cpu") die("--device=cpu: this backend has no CPU path (use the reference renderer)");
       size_t c = v.find(':');
       a.device = c == std::string::npos ? (v == "cuda" ? 0 : std::atoi(v.c_str())) : std::atoi(v.c_str() + c + 1);
-    } else if (s == "--ganesha-ply" || s == "-ganesha-ply") a.ply = need();
+    } else if (s == "--gpus") a.gpus = std::atoi(need().c_str());
+    else if (s == "--ganesha-ply" || s == "-ganesha-ply") a.ply = need();
     else if (s == "--synthetic-faces") a.synthetic_faces = std::atoll(need().c_str());
     else if (s == "--background") a.background = need();
     else die("unknown option '" + s + "'");
@@ -192,7 +193,8 @@ int main(int argc, char **argv) {
   if (ns) std::printf("#spheres = %lld\n", (long long)ns);
   if (nt) std::printf("#triangles = %lld\n", (long long)nt);
   double build_ms = 0;
-  check(ptb_scene_commit(sc, a.device, &build_ms), "commit");
+  if (a.gpus > 1) check(ptb_scene_commit_multi(sc, a.gpus, &build_ms), "commit");
+  else check(ptb_scene_commit(sc, a.device, &build_ms), "commit");
   int32_t ts[8];
   ptb_scene_tree_stats(sc, ts);
   std::printf("tree depth = %d\n", ts[1]);          // main.ml:263
@@ -205,7 +207,8 @@ int main(int argc, char **argv) {
   std::vector<double> image((size_t)3 * a.width * a.height);
   ptb_stats st;
   auto t0 = clk::now();
-  check(ptb_render(sc, &p, image.data(), &st), "render");
+  if (a.gpus > 1) check(ptb_render_multi(sc, &p, a.gpus, image.data(), &st), "render");
+  else check(ptb_render(sc, &p, image.data(), &st), "render");
   const double ms = std::chrono::duration<double, std::milli>(clk::now() - t0).count();
   // Bimage_unix.Stb.write of an f64 image: 8-bit, truncating (pinned by the sky rows of the golden PNG,
   // tests/golden/shirley_png_facts.json), clamped to [0, 255]

@@ -13,4 +13,7 @@ struct ptb_scene {
   std::vector<int32_t> ref_order;  // reference list order (see ptb_scene_get_prim_order); may be empty
   bool committed = false;
   ptb::DeviceState *dev = nullptr;
+  // ptb_scene_commit_multi: one replica per further device (device i+1 = replicas[i]); each shares this scene's
+  // tables and tree by value and owns its device copy
+  std::vector<ptb_scene *> replicas;
 };

@@ -1191,6 +1191,30 @@ __global__ void __launch_bounds__(256) k_resolve(const R *__restrict__ sums, OUT
   for (int c = 0; c < 3; ++c) out[3 * (size_t)p + c] = (OUT)(raw ? acc[c] : sqrt(acc[c] * spp_inv));
 }
 
+// Multi-GPU framebuffer reduce: device 0 adds the other devices' per-pixel sums into its own, reading them
+// straight out of peer memory (NVLink loads, 128-bit, coalesced) — no staging copy, no second pass.
+struct PeerPtrs {
+  const float *src[8];
+  int n;
+};
+__global__ void __launch_bounds__(256) k_reduce_peers(float *__restrict__ dst, PeerPtrs pp, size_t n) {
+  const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    float4 a = *reinterpret_cast<const float4 *>(dst + i);
+    for (int k = 0; k < pp.n; ++k) {
+      const float4 b = *reinterpret_cast<const float4 *>(pp.src[k] + i);
+      a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w;
+    }
+    *reinterpret_cast<float4 *>(dst + i) = a;
+  } else {
+    for (size_t j = i; j < n; ++j) {
+      float a = dst[j];
+      for (int k = 0; k < pp.n; ++k) a += pp.src[k][j];
+      dst[j] = a;
+    }
+  }
+}
+
 // R2 stream dump: out[i*D + d] = get(offsets[i], d), through the SAME device function as the pipeline
 __global__ void k_r2_stream(RenderConst rc, int D, const int32_t *__restrict__ offsets, long long n,
                             double *__restrict__ out) {

@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "handle.hpp"
@@ -538,6 +539,8 @@ using namespace ptb;
 
 extern "C" {
 
+static int upload_scene(ptb_scene *s, int32_t device);
+
 int ptb_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
@@ -567,6 +570,18 @@ int ptb_scene_commit(ptb_scene *s, int32_t device, double *ms) {
   // the traversal stack holds the tree's exact worst case + the sentinel; refuse trees it cannot hold rather
   // than dropping pushes on the device
   if (s->bvh.max_stack + 1 > 97) return fail(PTB_E_INVALID, "commit: tree too deep for the device traversal stack");
+  for (ptb_scene *r : s->replicas) ptb_scene_destroy(r);  // replicas of an older commit
+  s->replicas.clear();
+  if ((rc = upload_scene(s, device))) return rc;
+  if (ms) *ms = std::chrono::duration<double, std::milli>(clk::now() - t0).count();
+  return PTB_OK;
+}
+
+/* the device half of a commit: tables and tree of `s` (already built) onto `device` */
+static int upload_scene(ptb_scene *s, int32_t device) {
+  const HostScene &h = s->host;
+  int rc = check_device(device);
+  if (rc) return rc;
   if (s->dev) destroy_device_state(s->dev);
   s->dev = new DeviceState();
   DeviceState *d = s->dev;
@@ -597,7 +612,122 @@ int ptb_scene_commit(ptb_scene *s, int32_t device, double *ms) {
   s->committed = true;
   if ((rc = ensure_tables<float>(s))) return rc;
   CK(cudaDeviceSynchronize());
+  return PTB_OK;
+}
+
+/* Single-process multi-GPU: the scene is replicated on devices 0..n-1 (tree built once). */
+int ptb_scene_commit_multi(ptb_scene *s, int32_t n_devices, double *ms) {
+  using clk = std::chrono::steady_clock;
+  if (!s || n_devices < 1) return fail(PTB_E_INVALID, "commit_multi: bad args");
+  if (n_devices > ptb_device_count()) return fail(PTB_E_NO_DEVICE, "commit_multi: fewer CUDA devices than requested");
+  auto t0 = clk::now();
+  int rc = ptb_scene_commit(s, 0, nullptr);
+  if (rc) return rc;
+  for (int32_t i = 1; i < n_devices; ++i) {
+    ptb_scene *r = new ptb_scene();
+    r->host = s->host, r->bvh = s->bvh, r->ref_order = s->ref_order;
+    s->replicas.push_back(r);
+    if ((rc = upload_scene(r, i))) return rc;
+  }
+  check_device(0);
   if (ms) *ms = std::chrono::duration<double, std::milli>(clk::now() - t0).count();
+  return PTB_OK;
+}
+
+/* Integrator.render over n_devices GPUs of this process: device i renders the tiles t = i (mod n) of the
+ * reference's tile list into its own per-pixel sums (one host thread per device), device 0 then adds the other
+ * devices' sums straight out of their memory over NVLink (peer loads) and runs the filter + gamma resolve. */
+int ptb_render_multi(ptb_scene *s, const ptb_params *p, int32_t n_devices, double *image, ptb_stats *stats) {
+  using clk = std::chrono::steady_clock;
+  if (!s || !p || !image || n_devices < 1) return fail(PTB_E_INVALID, "render_multi: bad args");
+  if (p->flags & PTB_FLAG_F64) return fail(PTB_E_INVALID, "render_multi: float32 pipeline only");
+  if (!s->committed || !s->dev || s->dev->device != 0 || (int32_t)s->replicas.size() + 1 < n_devices)
+    return fail(PTB_E_STATE, "render_multi: scene is not committed on that many devices (call ptb_scene_commit_multi)");
+  if (n_devices > 8) return fail(PTB_E_INVALID, "render_multi: at most 8 devices");
+  auto t0 = clk::now();
+  const size_t n3 = (size_t)p->width * p->height * 3;
+  std::vector<int> rcs((size_t)n_devices, 0);
+  std::vector<std::string> msgs((size_t)n_devices);
+  std::vector<ptb_stats> st((size_t)n_devices);
+  std::vector<float *> sums((size_t)n_devices, nullptr);
+  auto one = [&](int i) {
+    ptb_scene *sc = i == 0 ? s : s->replicas[(size_t)i - 1];
+    auto body = [&]() -> int {
+      int rc = check_device(i);
+      if (rc) return rc;
+      DevicePool *pl = sc->dev->pool;
+      if (pl->sums_cap < n3 * sizeof(float)) {
+        cudaFree(pl->sums_buf);
+        pl->sums_buf = nullptr, pl->sums_cap = 0;
+        CK(cudaMalloc(&pl->sums_buf, n3 * sizeof(float)));
+        pl->sums_cap = n3 * sizeof(float);
+      }
+      sums[(size_t)i] = (float *)pl->sums_buf;
+      CK(cudaMemsetAsync(sums[(size_t)i], 0, n3 * sizeof(float), 0));
+      ptb_params q = *p;
+      q.device = i, q.tile_rank = i, q.tile_world = n_devices;
+      std::memset(&st[(size_t)i], 0, sizeof(ptb_stats));
+      return render_impl<float>(sc, q, sums[(size_t)i], 0, &st[(size_t)i]);  // synchronises its stream
+    };
+    rcs[(size_t)i] = body();
+    if (rcs[(size_t)i]) msgs[(size_t)i] = ptb_last_error();
+  };
+  std::vector<std::thread> th;
+  for (int i = 1; i < n_devices; ++i) th.emplace_back(one, i);
+  one(0);
+  for (auto &t : th) t.join();
+  for (int i = 0; i < n_devices; ++i)
+    if (rcs[(size_t)i]) return fail(rcs[(size_t)i], "render_multi: device " + std::to_string(i) + ": " + msgs[(size_t)i]);
+  // ---- framebuffer reduce on device 0 over peer memory, then resolve -------------------------------------
+  int rc = check_device(0);
+  if (rc) return rc;
+  DevicePool *pl0 = s->dev->pool;
+  PeerPtrs pp;
+  std::memset(&pp, 0, sizeof pp);
+  float *stage = nullptr;
+  for (int i = 1; i < n_devices; ++i) {
+    int can = 0;
+    CK(cudaDeviceCanAccessPeer(&can, 0, i));
+    if (can) {
+      cudaError_t e = cudaDeviceEnablePeerAccess(i, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(PTB_E_CUDA, std::string("peer access: ") + cudaGetErrorString(e));
+      cudaGetLastError();
+      pp.src[pp.n++] = sums[(size_t)i];
+    } else {  // no NVLink/PCIe peer path: stage the shard through a copy and add it
+      if (!stage) CK(cudaMalloc((void **)&stage, n3 * sizeof(float)));
+      CK(cudaMemcpyPeer(stage, 0, sums[(size_t)i], i, n3 * sizeof(float)));
+      PeerPtrs one_src;
+      std::memset(&one_src, 0, sizeof one_src);
+      one_src.src[0] = stage, one_src.n = 1;
+      k_reduce_peers<<<(unsigned)((n3 / 4 + 255) / 256), 256>>>(sums[0], one_src, n3);
+      CK(cudaDeviceSynchronize());
+    }
+  }
+  if (pp.n) k_reduce_peers<<<(unsigned)((n3 / 4 + 255) / 256), 256>>>(sums[0], pp, n3);
+  CK(cudaGetLastError());
+  if (stage) cudaFree(stage);
+  if (pl0->img_cap < n3 * sizeof(double)) {
+    cudaFree(pl0->img_buf);
+    pl0->img_buf = nullptr, pl0->img_cap = 0;
+    CK(cudaMalloc(&pl0->img_buf, n3 * sizeof(double)));
+    pl0->img_cap = n3 * sizeof(double);
+  }
+  rc = resolve_impl<float, double>(sums[0], (double *)pl0->img_buf, p->width, p->height, p->samples_per_pixel, p->flags, 0);
+  if (rc) return rc;
+  CK(cudaMemcpy(image, pl0->img_buf, n3 * sizeof(double), cudaMemcpyDeviceToHost));
+  if (stats) {
+    std::memset(stats, 0, sizeof *stats);
+    for (int i = 0; i < n_devices; ++i) {
+      const ptb_stats &a = st[(size_t)i];
+      stats->paths += a.paths, stats->rays += a.rays, stats->kernel_launches += a.kernel_launches;
+      for (int b = 0; b < MAX_BOUNCES; ++b) stats->rays_by_bounce[b] += a.rays_by_bounce[b];
+      stats->ms_device = std::max(stats->ms_device, a.ms_device);
+      stats->ms_trace = std::max(stats->ms_trace, a.ms_trace);
+    }
+    stats->kernel_launches += 2;
+    stats->d2h_bytes = n3 * sizeof(double);
+    stats->ms_total = std::chrono::duration<double, std::milli>(clk::now() - t0).count();
+  }
   return PTB_OK;
 }
 

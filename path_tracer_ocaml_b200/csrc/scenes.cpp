@@ -16,6 +16,7 @@ extern "C" {
 ptb_scene *ptb_scene_create(void) { return new (std::nothrow) ptb_scene(); }
 void ptb_scene_destroy(ptb_scene *s) {
   if (!s) return;
+  for (ptb_scene *r : s->replicas) ptb_scene_destroy(r);
   if (s->dev) destroy_device_state(s->dev);
   delete s;
 }

@@ -55,6 +55,16 @@ class Integrator:
         check(lib().ptb_render(self.scene.h, C.byref(p), dptr(image), C.byref(self.stats)))
         return image
 
+    # single-process multi-GPU: tiles dealt to n_devices GPUs, peer-memory reduce on device 0
+    def render_multi(self, n_devices, flags=0, image=None):
+        p = self._p(flags)
+        if getattr(self.scene, "n_devices", 1) < n_devices:
+            self.scene.commit_multi(n_devices)
+        if image is None:
+            image = np.empty((p.height, p.width, 3), dtype=np.float64)
+        check(lib().ptb_render_multi(self.scene.h, C.byref(p), n_devices, dptr(image), C.byref(self.stats)))
+        return image
+
     # device-resident path: adds this rank's per-pixel sums into a torch float32 CUDA tensor
     def render_device(self, sums, flags=0, stream=None):
         import torch

@@ -83,6 +83,13 @@ class Scene:
         self.committed_on, self.commit_ms = device, ms.value
         return ms.value
 
+    def commit_multi(self, n_devices):
+        """Replicates the committed scene on devices 0..n_devices-1 (single-process multi-GPU)."""
+        ms = C.c_double(0)
+        check(lib().ptb_scene_commit_multi(self.h, n_devices, C.byref(ms)))
+        self.committed_on, self.commit_ms, self.n_devices = 0, ms.value, n_devices
+        return ms.value
+
     def tree_stats(self):
         out = np.zeros(8, dtype=np.int32)
         check(lib().ptb_scene_tree_stats(self.h, iptr(out)))

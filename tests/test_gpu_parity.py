@@ -359,3 +359,21 @@ def test_full_size_properties_c4():
     big = torch.nn.functional.adaptive_avg_pool2d(img.cpu().permute(2, 0, 1)[None] ** 2, (360, 640))[0]
     sm = small_img.permute(2, 0, 1) ** 2
     assert (big[:, 4:-4, 4:-4] - sm[:, 4:-4, 4:-4]).abs().mean().item() < 0.02
+
+
+@pytest.mark.gpu
+def test_single_process_multi_gpu_render_equals_one_gpu():
+    """ptb_render_multi: tiles dealt to the GPUs of this process, peer-memory reduce on device 0.  Same image as
+    one GPU up to float summation order (skipped on a one-GPU box; the 1-device call must work anywhere)."""
+    W, H, spp, mb = 200, 120, 8, 8
+    ref = P.Integrator(P.shirley_spheres(W, H), W, H, spp, mb).render()
+    n = min(P.lib().ptb_device_count(), 4)
+    for k in sorted({1, n}):
+        sc = P.shirley_spheres(W, H)
+        integ = P.Integrator(sc, W, H, spp, mb)
+        img = integ.render_multi(k)
+        m = image_metrics(img, ref)
+        assert m["rmse"] < 2e-6 and m["max"] < 1e-4, (k, m)
+        assert integ.stats.paths == W * H * spp
+    with pytest.raises(P.PtbError):
+        P.Integrator(P.shirley_spheres(W, H), W, H, spp, mb).render_multi(P.lib().ptb_device_count() + 1)
