@@ -11,6 +11,7 @@
 
 #include "handle.hpp"
 #include "kernels.cuh"
+#include "gpu_bvh.cuh"
 
 namespace ptb {
 
@@ -159,6 +160,8 @@ static int ensure_tables(ptb_scene *s) {
   if (t.ready) return PTB_OK;
   const HostScene &h = s->host;
   const WideBVH &b = s->bvh;
+  if (b.device_built)
+    return fail(PTB_E_UNSUPPORTED, "this scene's tree was built on the device (float32 tables only): use PTB_BUILDER=host for PTB_FLAG_F64");
   std::vector<Node4<R>> nodes(b.nodes.size());
   for (size_t i = 0; i < nodes.size(); ++i) {
     for (int k = 0; k < 4; ++k) {
@@ -280,9 +283,9 @@ static DScene<R> make_dscene(ptb_scene *s, size_t *scene_bytes_out) {
   sc.sphere_id = d->sphere_id, sc.tri_id = d->tri_id, sc.sphere_mat = d->sphere_mat, sc.tri_mat = d->tri_mat;
   sc.tri_uv = t.tri_uv, sc.mats = d->mats, sc.texs = t.texs;
   sc.prim_kind = d->prim_kind;
-  sc.n_nodes = (int)s->bvh.nodes.size();
+  sc.n_nodes = (int)s->bvh.node_count();
   sc.n_spheres = (int)s->bvh.sphere_order.size();
-  sc.n_tris = (int)s->bvh.tri_order.size();
+  sc.n_tris = (int)s->bvh.tri_count();
   size_t bytes = (size_t)sc.n_nodes * sizeof(Node4<R>) + (size_t)sc.n_spheres * sizeof(Vec4<R>) +
                  (size_t)sc.n_tris * 3 * sizeof(Vec4<R>) + (((size_t)sc.n_spheres + sc.n_tris + 15) / 16) * 16;
   // entry 0 of the traversal stack is the sentinel.  A tree whose worst case fits gets an unchecked stack
@@ -526,6 +529,161 @@ static int render_host_impl(ptb_scene *s, const ptb_params &p, double *image, pt
   return rc;
 }
 
+static int new_device_state(ptb_scene *s, int device) {
+  int rc = check_device(device);
+  if (rc) return rc;
+  DeviceState *d = new DeviceState();
+  s->dev = d;
+  d->device = device;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  d->sm_count = prop.multiProcessorCount;
+  d->smem_optin = prop.sharedMemPerBlockOptin;
+  d->pool = pool_for(device);
+  if (!d->pool->ctl) {
+    CK(cudaMalloc((void **)&d->pool->ctl, sizeof(Ctl)));
+    CK(cudaMemset(d->pool->ctl, 0, sizeof(Ctl)));
+  }
+  return PTB_OK;
+}
+
+// ---- device-side tree build for big triangle meshes (gpu_bvh.cuh) ------------------------------------------------
+static bool want_gpu_builder(const HostScene &h) {
+  if (h.n_spheres() != 0 || h.n_tris() < 2) return false;  // pure triangle meshes only
+  if (const char *e = std::getenv("PTB_BUILDER")) {
+    if (!std::strcmp(e, "host")) return false;
+    if (!std::strcmp(e, "gpu")) return true;
+  }
+  return h.n_tris() >= 200000;  // below that the host SAH build is a few tens of ms and its tree is better
+}
+
+// Builds tree + float32 tables of `s` on s->dev->device.  Returns PTB_OK, or a positive value when the mesh
+// cannot be handled here (tree too deep for the traversal stack) and the host builder should take over.
+static int gpu_build_mesh(ptb_scene *s) {
+  using namespace gbvh;
+  DeviceState *d = s->dev;
+  const HostScene &h = s->host;
+  const int n = (int)h.n_tris();
+  const size_t nv = h.vx.size();
+  double *vx = nullptr, *vy = nullptr, *vz = nullptr, *tuv = nullptr;
+  int32_t *idx = nullptr, *tmat = nullptr;
+  uint8_t *mkind = nullptr;
+  float4 *blo = nullptr, *bhi = nullptr, *nlo = nullptr, *nhi = nullptr;
+  Bounds6 *cb = nullptr;
+  unsigned long long *k0 = nullptr, *k1 = nullptr;
+  unsigned *v0 = nullptr, *v1 = nullptr, *visits = nullptr;
+  int *lch = nullptr, *rch = nullptr, *first = nullptr, *count = nullptr, *pari = nullptr, *parl = nullptr, *counters = nullptr;
+  Frontier *fa = nullptr, *fb = nullptr;
+  Node4<float> *tmp_nodes = nullptr;
+  void *cub_tmp = nullptr;
+  std::vector<void *> to_free;
+  auto A = [&](auto **p, size_t count_) -> int {
+    CK(cudaMalloc((void **)p, std::max<size_t>(count_, 1) * sizeof(**p)));
+    to_free.push_back((void *)*p);
+    return PTB_OK;
+  };
+  auto cleanup = [&]() {
+    for (void *p : to_free) cudaFree(p);
+  };
+  int rc = PTB_OK;
+#define G(x)            \
+  if ((rc = (x))) {     \
+    cleanup();          \
+    return rc;          \
+  }
+  G(A(&vx, nv)) G(A(&vy, nv)) G(A(&vz, nv)) G(A(&idx, 3 * (size_t)n)) G(A(&tmat, (size_t)n)) G(A(&tuv, 6 * (size_t)n))
+  G(A(&mkind, h.mat.size())) G(A(&blo, (size_t)n)) G(A(&bhi, (size_t)n)) G(A(&nlo, (size_t)n)) G(A(&nhi, (size_t)n)) G(A(&cb, 1))
+  G(A(&k0, (size_t)n)) G(A(&k1, (size_t)n)) G(A(&v0, (size_t)n)) G(A(&v1, (size_t)n)) G(A(&visits, (size_t)n))
+  G(A(&lch, (size_t)n)) G(A(&rch, (size_t)n)) G(A(&first, (size_t)n)) G(A(&count, (size_t)n)) G(A(&pari, (size_t)n)) G(A(&parl, (size_t)n))
+  G(A(&counters, 4)) G(A(&fa, (size_t)n)) G(A(&fb, (size_t)n)) G(A(&tmp_nodes, (size_t)n))
+  auto H2D = [&](void *dst, const void *src, size_t bytes) -> int {
+    CK(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+    return PTB_OK;
+  };
+  std::vector<uint8_t> mk(h.mat.size());
+  for (size_t i = 0; i < mk.size(); ++i) mk[i] = (uint8_t)h.mat[i].kind;
+  G(H2D(vx, h.vx.data(), nv * 8)) G(H2D(vy, h.vy.data(), nv * 8)) G(H2D(vz, h.vz.data(), nv * 8))
+  G(H2D(idx, h.tidx.data(), 3 * (size_t)n * 4)) G(H2D(tmat, h.tmat.data(), (size_t)n * 4)) G(H2D(tuv, h.tuv.data(), 6 * (size_t)n * 8))
+  G(H2D(mkind, mk.data(), mk.size()))
+  Bounds6 cb0;
+  for (int k = 0; k < 3; ++k) cb0.lo[k] = 0xffffffffu, cb0.hi[k] = 0u;
+  G(H2D(cb, &cb0, sizeof cb0))
+  const unsigned gb = (unsigned)((n + 255) / 256);
+  k_tri_boxes<<<gb, 256>>>(vx, vy, vz, idx, n, blo, bhi, cb);
+  k_morton<<<gb, 256>>>(blo, bhi, n, cb, k0, v0);
+  size_t cub_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, k0, k1, v0, v1, n, 0, 63);
+  G(A((char **)&cub_tmp, cub_bytes))
+  cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, k0, k1, v0, v1, n, 0, 63);
+  k_radix_tree<<<gb, 256>>>(k1, n, lch, rch, first, count, pari, parl);
+  if (cudaMemset(visits, 0, (size_t)n * 4) != cudaSuccess || cudaMemset(counters, 0, 16) != cudaSuccess) {
+    cleanup();
+    return fail(PTB_E_CUDA, "gpu build: memset failed");
+  }
+  k_fit<<<gb, 256>>>(v1, blo, bhi, n, lch, rch, pari, parl, visits, nlo, nhi);
+  // collapse, level by level from the root (binary node 0 = wide node 0)
+  Frontier root{0, 0};
+  G(H2D(fa, &root, sizeof root))
+  int hc[4] = {1, 0, 0, 0};
+  G(H2D(counters, hc, sizeof hc))
+  int n_cur = 1, levels = 0;
+  while (n_cur > 0) {
+    ++levels;
+    k_collapse_level<<<(unsigned)((n_cur + 127) / 128), 128>>>(fa, n_cur, lch, rch, first, count, v1, blo, bhi, nlo, nhi, tmp_nodes, fb,
+                                                             counters);
+    if (cudaMemcpy(hc, counters, sizeof hc, cudaMemcpyDeviceToHost) != cudaSuccess) {
+      cudaError_t e = cudaGetLastError();
+      cleanup();
+      return fail(PTB_E_CUDA, std::string("gpu build: ") + cudaGetErrorString(e));
+    }
+    n_cur = hc[1];
+    const int zero = 0;
+    G(H2D(counters + 1, &zero, 4))
+    std::swap(fa, fb);
+    if (3 * levels + 1 > 97) {  // deeper than the traversal stack can hold: let the host builder do this mesh
+      cleanup();
+      return 1;
+    }
+  }
+  const int n_wide = hc[0];
+  // outputs
+  Tables<float> &t = d->tf;
+  free_tables(t);
+  cudaFree(d->sphere_id), cudaFree(d->tri_id), cudaFree(d->sphere_mat), cudaFree(d->tri_mat), cudaFree(d->mats), cudaFree(d->prim_kind);
+  d->sphere_id = d->tri_id = d->sphere_mat = d->tri_mat = nullptr, d->mats = nullptr, d->prim_kind = nullptr;
+  auto OUT = [&](auto **p, size_t count_) -> int {
+    CK(cudaMalloc((void **)p, std::max<size_t>(count_, 1) * sizeof(**p)));
+    return PTB_OK;
+  };
+  G(OUT(&t.nodes, (size_t)n_wide)) G(OUT(&t.spheres, 1)) G(OUT(&t.tris, 3 * (size_t)n)) G(OUT(&t.tri_uv, 6 * (size_t)n))
+  G(OUT(&d->sphere_id, 1)) G(OUT(&d->sphere_mat, 1)) G(OUT(&d->tri_id, (size_t)n)) G(OUT(&d->tri_mat, (size_t)n))
+  G(OUT(&d->prim_kind, ((size_t)n + 15) / 16 * 16 + 16))
+  if (cudaMemcpy(t.nodes, tmp_nodes, (size_t)n_wide * sizeof(Node4<float>), cudaMemcpyDeviceToDevice) != cudaSuccess ||
+      cudaMemset(d->prim_kind, 0, ((size_t)n + 15) / 16 * 16 + 16) != cudaSuccess) {
+    cleanup();
+    return fail(PTB_E_CUDA, "gpu build: copy failed");
+  }
+  k_emit_tris<<<gb, 256>>>(v1, n, vx, vy, vz, idx, tmat, tuv, mkind, t.tris, t.tri_uv, d->tri_id, d->tri_mat, d->prim_kind);
+  std::vector<DTex<float>> texs(h.tex.size());
+  for (size_t i = 0; i < texs.size(); ++i) {
+    const ptb_texture &x = h.tex[i];
+    texs[i] = {x.kind, x.width, x.height, x.even, x.odd, 0, {(float)x.rgb[0], (float)x.rgb[1], (float)x.rgb[2]}};
+  }
+  std::vector<DMat> mats(h.mat.size());
+  for (size_t i = 0; i < mats.size(); ++i) mats[i] = {h.mat[i].kind, h.mat[i].texture, h.mat[i].index};
+  G(upload(&t.texs, texs)) G(upload(&d->mats, mats))
+  cudaError_t e = cudaDeviceSynchronize();
+  cleanup();
+  if (e != cudaSuccess) return fail(PTB_E_CUDA, std::string("gpu build: ") + cudaGetErrorString(e));
+#undef G
+  t.ready = true;
+  WideBVH &b = s->bvh;
+  b.nodes.clear(), b.sphere_order.clear(), b.tri_order.clear();
+  b.device_built = true, b.dev_nodes = n_wide, b.dev_tris = n, b.dev_leaves = hc[2];
+  b.depth = levels, b.max_stack = 3 * levels;
+  return PTB_OK;
+}
+
 static int require_committed(ptb_scene *s, int device) {
   if (!s) return fail(PTB_E_INVALID, "null scene");
   if (!s->committed || !s->dev) return fail(PTB_E_STATE, "scene is not committed (call ptb_scene_commit)");
@@ -566,12 +724,27 @@ int ptb_scene_commit(ptb_scene *s, int32_t device, double *ms) {
   int rc = check_device(device);
   if (rc) return rc;
   auto t0 = clk::now();
+  for (ptb_scene *r : s->replicas) ptb_scene_destroy(r);  // replicas of an older commit
+  s->replicas.clear();
+  s->bvh = WideBVH();
+  bool built = false;
+  if (want_gpu_builder(h)) {  // big pure-triangle mesh: build the tree on the device
+    if (s->dev) destroy_device_state(s->dev);
+    s->dev = nullptr;
+    if ((rc = new_device_state(s, device))) return rc;
+    rc = gpu_build_mesh(s);
+    if (rc < 0) return rc;
+    built = rc == PTB_OK;
+    if (built) {
+      s->committed = true;
+      if (ms) *ms = std::chrono::duration<double, std::milli>(clk::now() - t0).count();
+      return PTB_OK;
+    }
+  }
   build_wide_bvh(h, &s->bvh);
   // the traversal stack holds the tree's exact worst case + the sentinel; refuse trees it cannot hold rather
   // than dropping pushes on the device
   if (s->bvh.max_stack + 1 > 97) return fail(PTB_E_INVALID, "commit: tree too deep for the device traversal stack");
-  for (ptb_scene *r : s->replicas) ptb_scene_destroy(r);  // replicas of an older commit
-  s->replicas.clear();
   if ((rc = upload_scene(s, device))) return rc;
   if (ms) *ms = std::chrono::duration<double, std::milli>(clk::now() - t0).count();
   return PTB_OK;
@@ -583,13 +756,9 @@ static int upload_scene(ptb_scene *s, int32_t device) {
   int rc = check_device(device);
   if (rc) return rc;
   if (s->dev) destroy_device_state(s->dev);
-  s->dev = new DeviceState();
+  s->dev = nullptr;
+  if ((rc = new_device_state(s, device))) return rc;
   DeviceState *d = s->dev;
-  d->device = device;
-  cudaDeviceProp prop;
-  CK(cudaGetDeviceProperties(&prop, device));
-  d->sm_count = prop.multiProcessorCount;
-  d->smem_optin = prop.sharedMemPerBlockOptin;
   std::vector<int32_t> smat(s->bvh.sphere_order.size()), tmat(s->bvh.tri_order.size());
   for (size_t k = 0; k < smat.size(); ++k) smat[k] = h.smat[s->bvh.sphere_order[k]];
   for (size_t k = 0; k < tmat.size(); ++k) tmat[k] = h.tmat[s->bvh.tri_order[k]];
@@ -604,11 +773,6 @@ static int upload_scene(ptb_scene *s, int32_t device) {
   for (size_t k = 0; k < smat.size(); ++k) kinds[k] = (uint8_t)h.mat[smat[k]].kind;
   for (size_t k = 0; k < tmat.size(); ++k) kinds[smat.size() + k] = (uint8_t)h.mat[tmat[k]].kind;
   if ((rc = upload(&d->prim_kind, kinds))) return rc;
-  d->pool = pool_for(device);
-  if (!d->pool->ctl) {
-    CK(cudaMalloc((void **)&d->pool->ctl, sizeof(Ctl)));
-    CK(cudaMemset(d->pool->ctl, 0, sizeof(Ctl)));
-  }
   s->committed = true;
   if ((rc = ensure_tables<float>(s))) return rc;
   CK(cudaDeviceSynchronize());
@@ -627,7 +791,16 @@ int ptb_scene_commit_multi(ptb_scene *s, int32_t n_devices, double *ms) {
     ptb_scene *r = new ptb_scene();
     r->host = s->host, r->bvh = s->bvh, r->ref_order = s->ref_order;
     s->replicas.push_back(r);
-    if ((rc = upload_scene(r, i))) return rc;
+    if (s->bvh.device_built) {  // the device builder is deterministic: every replica builds the same tree
+      r->bvh = WideBVH();
+      if ((rc = new_device_state(r, i))) return rc;
+      rc = gpu_build_mesh(r);
+      if (rc > 0) rc = fail(PTB_E_STATE, "commit_multi: device build refused on a replica");
+      if (rc) return rc;
+      r->committed = true;
+    } else if ((rc = upload_scene(r, i))) {
+      return rc;
+    }
   }
   check_device(0);
   if (ms) *ms = std::chrono::duration<double, std::milli>(clk::now() - t0).count();
@@ -735,12 +908,12 @@ int ptb_scene_tree_stats(const ptb_scene *s, int32_t out[8]) {
   if (!s || !out) return fail(PTB_E_INVALID, "tree_stats: null argument");
   if (!s->committed) return fail(PTB_E_STATE, "scene is not committed (call ptb_scene_commit)");
   std::memset(out, 0, 8 * sizeof(int32_t));
-  out[0] = (int32_t)s->bvh.nodes.size();
+  out[0] = (int32_t)s->bvh.node_count();
   out[1] = s->bvh.depth;
   out[2] = s->bvh.max_stack;
   out[3] = (int32_t)s->bvh.sphere_order.size();
-  out[4] = (int32_t)s->bvh.tri_order.size();
-  int leaves = 0;
+  out[4] = (int32_t)s->bvh.tri_count();
+  int leaves = (int)s->bvh.dev_leaves;
   for (const WideNode &n : s->bvh.nodes)
     for (int k = 0; k < 4; ++k)
       if (n.child[k] < 0 && n.child[k] != EMPTY_CHILD) ++leaves;

@@ -57,6 +57,11 @@ struct WideBVH {
   std::vector<int32_t> tri_order;     // device slot -> triangle index as set by the caller
   int depth = 0;                   // inner levels
   int max_stack = 0;               // worst-case traversal stack entries
+  // tree built on the device (gpu_bvh.cuh): `nodes` / `tri_order` stay empty, only the counts are known here
+  bool device_built = false;
+  int64_t dev_nodes = 0, dev_tris = 0, dev_leaves = 0;
+  int64_t node_count() const { return device_built ? dev_nodes : (int64_t)nodes.size(); }
+  int64_t tri_count() const { return device_built ? dev_tris : (int64_t)tri_order.size(); }
 };
 
 struct HostScene {

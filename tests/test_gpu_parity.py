@@ -124,6 +124,37 @@ def test_first_hit_map_big_mesh_threaded_tree_build():
     assert st["triangles"] >= 140000 and st["max_stack"] + 1 <= 97
 
 
+@pytest.fixture
+def gpu_builder(monkeypatch):
+    monkeypatch.setenv("PTB_BUILDER", "gpu")
+
+
+def test_device_built_tree_first_hit_and_image_parity(gpu_builder):
+    """gpu_bvh.cuh (Morton sort + radix tree + collapse on the device): closest hits do not depend on the tree."""
+    scene = P.synthetic_mesh_scene(60000, 240, 135)
+    _first_hit_check(scene, 240, 135, prim_frac=0.99)
+    st = scene.tree_stats()
+    assert st["triangles"] >= 55000 and st["nodes"] > 1000 and st["max_stack"] + 1 <= 97, st
+    integ = P.Integrator(scene, 240, 135, 8, 8)
+    img = integ.render()
+    ref, cn = O.OracleScene(scene.tables()).render(integ.params, n_threads=os.cpu_count())
+    m = image_metrics(img, ref)
+    assert m["rmse"] < 0.01 and m["within"] > 0.99, m
+    assert abs(int(integ.stats.rays) - int(cn.rays)) / cn.rays < 2e-3
+    with pytest.raises(P.PtbError):  # float64 validation mode needs the host-built tree
+        integ.render(flags=capi.PTB_FLAG_F64)
+
+
+def test_device_and_host_built_trees_render_the_same_image(monkeypatch):
+    imgs = {}
+    for b in ("host", "gpu"):
+        monkeypatch.setenv("PTB_BUILDER", b)
+        sc = P.synthetic_mesh_scene(30000, 160, 90)
+        imgs[b] = P.Integrator(sc, 160, 90, 16, 8).render()
+    m = image_metrics(imgs["gpu"], imgs["host"])
+    assert m["rmse"] < 2e-3, m  # same closest hits; float tie-breaks / atomics order differ
+
+
 def _random_rays(rng, n, lo, hi):
     o = rng.uniform(lo, hi, size=(n, 3))
     d = rng.normal(size=(n, 3))
