@@ -552,13 +552,17 @@ static bool want_gpu_builder(const HostScene &h) {
   if (h.n_spheres() != 0 || h.n_tris() < 2) return false;  // pure triangle meshes only
   if (const char *e = std::getenv("PTB_BUILDER")) {
     if (!std::strcmp(e, "host")) return false;
-    if (!std::strcmp(e, "gpu")) return true;
+    if (!std::strcmp(e, "gpu") || !std::strcmp(e, "gpu-lbvh") || !std::strcmp(e, "gpu-sah")) return true;
   }
   return h.n_tris() >= 200000;  // below that the host SAH build is a few tens of ms and its tree is better
 }
 
 // Builds tree + float32 tables of `s` on s->dev->device.  Returns PTB_OK, or a positive value when the mesh
 // cannot be handled here (tree too deep for the traversal stack) and the host builder should take over.
+static bool gpu_builder_sah() {  // PTB_BUILDER=gpu-lbvh selects the linear builder, anything else the binned-SAH one
+  const char *e = std::getenv("PTB_BUILDER");
+  return !(e && !std::strcmp(e, "gpu-lbvh"));
+}
 static int gpu_build_mesh(ptb_scene *s) {
   using namespace gbvh;
   DeviceState *d = s->dev;
@@ -592,10 +596,13 @@ static int gpu_build_mesh(ptb_scene *s) {
     return rc;          \
   }
   G(A(&vx, nv)) G(A(&vy, nv)) G(A(&vz, nv)) G(A(&idx, 3 * (size_t)n)) G(A(&tmat, (size_t)n)) G(A(&tuv, 6 * (size_t)n))
-  G(A(&mkind, h.mat.size())) G(A(&blo, (size_t)n)) G(A(&bhi, (size_t)n)) G(A(&nlo, (size_t)n)) G(A(&nhi, (size_t)n)) G(A(&cb, 1))
-  G(A(&k0, (size_t)n)) G(A(&k1, (size_t)n)) G(A(&v0, (size_t)n)) G(A(&v1, (size_t)n)) G(A(&visits, (size_t)n))
-  G(A(&lch, (size_t)n)) G(A(&rch, (size_t)n)) G(A(&first, (size_t)n)) G(A(&count, (size_t)n)) G(A(&pari, (size_t)n)) G(A(&parl, (size_t)n))
+  const bool sah = gpu_builder_sah();
+  const size_t nn = sah ? 2 * (size_t)n + 2 : (size_t)n;  // binary nodes
+  G(A(&mkind, h.mat.size())) G(A(&blo, (size_t)n)) G(A(&bhi, (size_t)n)) G(A(&nlo, nn)) G(A(&nhi, nn)) G(A(&cb, 2))
+  G(A(&k0, (size_t)n)) G(A(&k1, (size_t)n)) G(A(&v0, (size_t)n)) G(A(&v1, (size_t)n)) G(A(&visits, nn))
+  G(A(&lch, nn)) G(A(&rch, nn)) G(A(&first, nn)) G(A(&count, nn)) G(A(&pari, nn)) G(A(&parl, nn))
   G(A(&counters, 4)) G(A(&fa, (size_t)n)) G(A(&fb, (size_t)n)) G(A(&tmp_nodes, (size_t)n))
+  (void)visits;
   auto H2D = [&](void *dst, const void *src, size_t bytes) -> int {
     CK(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
     return PTB_OK;
@@ -605,22 +612,75 @@ static int gpu_build_mesh(ptb_scene *s) {
   G(H2D(vx, h.vx.data(), nv * 8)) G(H2D(vy, h.vy.data(), nv * 8)) G(H2D(vz, h.vz.data(), nv * 8))
   G(H2D(idx, h.tidx.data(), 3 * (size_t)n * 4)) G(H2D(tmat, h.tmat.data(), (size_t)n * 4)) G(H2D(tuv, h.tuv.data(), 6 * (size_t)n * 8))
   G(H2D(mkind, mk.data(), mk.size()))
-  Bounds6 cb0;
-  for (int k = 0; k < 3; ++k) cb0.lo[k] = 0xffffffffu, cb0.hi[k] = 0u;
-  G(H2D(cb, &cb0, sizeof cb0))
+  Bounds6 cb0[2];
+  for (int q = 0; q < 2; ++q)
+    for (int k = 0; k < 3; ++k) cb0[q].lo[k] = 0xffffffffu, cb0[q].hi[k] = 0u;
+  G(H2D(cb, cb0, sizeof cb0))
   const unsigned gb = (unsigned)((n + 255) / 256);
   k_tri_boxes<<<gb, 256>>>(vx, vy, vz, idx, n, blo, bhi, cb);
-  k_morton<<<gb, 256>>>(blo, bhi, n, cb, k0, v0);
   size_t cub_bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, k0, k1, v0, v1, n, 0, 63);
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, k0, k1, v0, v1, n, 0, 64);
   G(A((char **)&cub_tmp, cub_bytes))
-  cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, k0, k1, v0, v1, n, 0, 63);
-  k_radix_tree<<<gb, 256>>>(k1, n, lch, rch, first, count, pari, parl);
-  if (cudaMemset(visits, 0, (size_t)n * 4) != cudaSuccess || cudaMemset(counters, 0, 16) != cudaSuccess) {
+  if (cudaMemset(visits, 0, nn * 4) != cudaSuccess || cudaMemset(counters, 0, 16) != cudaSuccess) {
     cleanup();
     return fail(PTB_E_CUDA, "gpu build: memset failed");
   }
-  k_fit<<<gb, 256>>>(v1, blo, bhi, n, lch, rch, pari, parl, visits, nlo, nhi);
+  int leaf_thresh = GLEAF;
+  if (!sah) {
+    k_morton<<<gb, 256>>>(blo, bhi, n, cb, k0, v0);
+    cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, k0, k1, v0, v1, n, 0, 63);
+    k_radix_tree<<<gb, 256>>>(k1, n, lch, rch, first, count, pari, parl);
+    k_fit<<<gb, 256>>>(v1, blo, bhi, n, lch, rch, pari, parl, visits, nlo, nhi);
+  } else {
+    // binned SAH, level by level (gpu_bvh.cuh).  pari = slot, parl = axis, rch.. map onto the SahTree fields
+    int *node_id = nullptr, *act_a = nullptr, *act_b = nullptr, *split = nullptr, *level_of = nullptr;
+    unsigned *bins = nullptr;
+    const size_t max_active = (size_t)n / (GLEAF + 1) + 4;
+    G(A(&node_id, (size_t)n)) G(A(&act_a, max_active)) G(A(&act_b, max_active)) G(A(&split, nn)) G(A(&level_of, nn))
+    G(A(&bins, max_active * NODE_BINS))
+    SahTree T{nlo, nhi, count, first, lch, rch, pari, parl, split, level_of, visits};
+    Bounds6 hb[2];
+    if (cudaMemcpy(hb, cb, sizeof hb, cudaMemcpyDeviceToHost) != cudaSuccess || cudaMemset(node_id, 0, (size_t)n * 4) != cudaSuccess ||
+        cudaMemset(k0, 0, (size_t)n * 8) != cudaSuccess) {
+      cleanup();
+      return fail(PTB_E_CUDA, "gpu build: setup failed");
+    }
+    const float4 rlo = make_float4(dec_f(hb[1].lo[0]), dec_f(hb[1].lo[1]), dec_f(hb[1].lo[2]), 0.f);
+    const float4 rhi = make_float4(dec_f(hb[1].hi[0]), dec_f(hb[1].hi[1]), dec_f(hb[1].hi[2]), 0.f);
+    const int i_n = n, i_zero = 0, i_m1 = -1, i_max = INT32_MAX;
+    G(H2D(nlo, &rlo, 16)) G(H2D(nhi, &rhi, 16)) G(H2D(count, &i_n, 4)) G(H2D(first, &i_max, 4)) G(H2D(lch, &i_m1, 4))
+    G(H2D(rch, &i_m1, 4)) G(H2D(pari, &i_zero, 4)) G(H2D(level_of, &i_m1, 4)) G(H2D(act_a, &i_zero, 4))
+    int hcs[4] = {1, 0, 0, 0};
+    G(H2D(counters, hcs, sizeof hcs))
+    int n_active = 1;
+    for (int level = 0; n_active > 0; ++level) {
+      if (level >= 63) {  // path key exhausted: not a mesh for this builder
+        cleanup();
+        return 1;
+      }
+      k_sah_clear<<<(unsigned)(((size_t)n_active * 3 * SB + 255) / 256), 256>>>(bins, n_active);
+      if (n_active <= 4) k_sah_bin<true><<<gb, 256>>>(blo, bhi, n, node_id, T, bins);
+      else k_sah_bin<false><<<gb, 256>>>(blo, bhi, n, node_id, T, bins);
+      k_sah_select<<<(unsigned)(((size_t)n_active * 32 + 255) / 256), 256>>>(act_a, n_active, bins, T, level, act_b, counters);
+      k_sah_assign<<<gb, 256>>>(blo, bhi, n, node_id, k0, T, level);
+      if (cudaMemcpy(hcs, counters, sizeof hcs, cudaMemcpyDeviceToHost) != cudaSuccess) {
+        cudaError_t e = cudaGetLastError();
+        cleanup();
+        return fail(PTB_E_CUDA, std::string("gpu build (sah): ") + cudaGetErrorString(e));
+      }
+      n_active = hcs[1];
+      G(H2D(counters + 1, &i_zero, 4))
+      std::swap(act_a, act_b);
+    }
+    k_iota<<<gb, 256>>>(v0, n);
+    cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, k0, k1, v0, v1, n, 0, 64);
+    k_sah_first<<<gb, 256>>>(v1, n, node_id, first);
+    leaf_thresh = 0;
+    if (cudaMemset(counters, 0, 16) != cudaSuccess) {
+      cleanup();
+      return fail(PTB_E_CUDA, "gpu build: memset failed");
+    }
+  }
   // collapse, level by level from the root (binary node 0 = wide node 0)
   Frontier root{0, 0};
   G(H2D(fa, &root, sizeof root))
@@ -630,7 +690,7 @@ static int gpu_build_mesh(ptb_scene *s) {
   while (n_cur > 0) {
     ++levels;
     k_collapse_level<<<(unsigned)((n_cur + 127) / 128), 128>>>(fa, n_cur, lch, rch, first, count, v1, blo, bhi, nlo, nhi, tmp_nodes, fb,
-                                                             counters);
+                                                             counters, leaf_thresh);
     if (cudaMemcpy(hc, counters, sizeof hc, cudaMemcpyDeviceToHost) != cudaSuccess) {
       cudaError_t e = cudaGetLastError();
       cleanup();

@@ -5,7 +5,7 @@ import path_tracer_ocaml_b200 as P
 from path_tracer_ocaml_b200 import capi
 W, H, SPP = 1920, 1080, 256
 for nf in (100000, 1000000, 4000000):
-    for builder in ("host", "gpu"):
+    for builder in ("host", "gpu-lbvh", "gpu-sah"):
         os.environ["PTB_BUILDER"] = builder
         sc = P.synthetic_mesh_scene(nf, W, H)
         ts = []
@@ -16,4 +16,4 @@ for nf in (100000, 1000000, 4000000):
         for i in range(2):
             integ.render(); best = min(best, integ.stats.ms_device)
         st = integ.stats
-        print(f"{nf:8d} faces {builder:4s}: commit ms {min(ts):8.1f}  render {best:7.1f} ms  {st.paths/best/1e3:7.0f} Mpaths/s {st.rays/best/1e3:7.0f} Mrays/s  {sc.tree_stats()}", flush=True)
+        print(f"{nf:8d} faces {builder:8s}: commit ms {min(ts):8.1f}  render {best:7.1f} ms  {st.paths/best/1e3:7.0f} Mpaths/s {st.rays/best/1e3:7.0f} Mrays/s  {sc.tree_stats()}", flush=True)

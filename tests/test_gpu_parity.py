@@ -124,13 +124,14 @@ def test_first_hit_map_big_mesh_threaded_tree_build():
     assert st["triangles"] >= 140000 and st["max_stack"] + 1 <= 97
 
 
-@pytest.fixture
-def gpu_builder(monkeypatch):
-    monkeypatch.setenv("PTB_BUILDER", "gpu")
+@pytest.fixture(params=["gpu-sah", "gpu-lbvh"])
+def gpu_builder(request, monkeypatch):
+    monkeypatch.setenv("PTB_BUILDER", request.param)
 
 
 def test_device_built_tree_first_hit_and_image_parity(gpu_builder):
-    """gpu_bvh.cuh (Morton sort + radix tree + collapse on the device): closest hits do not depend on the tree."""
+    """gpu_bvh.cuh (binned SAH level by level, or Morton sort + radix tree, then the 4-wide collapse, all on the
+    device): closest hits do not depend on the tree."""
     scene = P.synthetic_mesh_scene(60000, 240, 135)
     _first_hit_check(scene, 240, 135, prim_frac=0.99)
     st = scene.tree_stats()
@@ -147,12 +148,13 @@ def test_device_built_tree_first_hit_and_image_parity(gpu_builder):
 
 def test_device_and_host_built_trees_render_the_same_image(monkeypatch):
     imgs = {}
-    for b in ("host", "gpu"):
+    for b in ("host", "gpu", "gpu-lbvh"):
         monkeypatch.setenv("PTB_BUILDER", b)
         sc = P.synthetic_mesh_scene(30000, 160, 90)
         imgs[b] = P.Integrator(sc, 160, 90, 16, 8).render()
-    m = image_metrics(imgs["gpu"], imgs["host"])
-    assert m["rmse"] < 2e-3, m  # same closest hits; float tie-breaks / atomics order differ
+    for b in ("gpu", "gpu-lbvh"):
+        m = image_metrics(imgs[b], imgs["host"])
+        assert m["rmse"] < 2e-3, (b, m)  # same closest hits; float tie-breaks / atomics order differ
 
 
 def _random_rays(rng, n, lo, hi):
