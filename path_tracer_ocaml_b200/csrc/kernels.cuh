@@ -208,7 +208,7 @@ __device__ __forceinline__ void tri_test(Vec4<R> v0, Vec4<R> e1v, Vec4<R> e2v, V
   V3<R> pvec = cross(d, e2);
   R det = dot(e1, pvec);
   if (r_abs(det) < R(1e-6)) return;
-  R inv = R(1) / det;
+  R inv = r_rcp(det);  // float: one MUFU.RCP (|det| >= 1e-6, far from the flush-to-zero range); double: exact
   V3<R> tvec = {o.x - v0.x, o.y - v0.y, o.z - v0.z};
   R u = inv * dot(tvec, pvec);
   V3<R> qvec = cross(tvec, e1);
