@@ -10,5 +10,5 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 PTB_BATCH=8388608 python bench.py --spp 2 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/plain2.log 2>&1 &&
 PTB_BATCH=8388608 ncu --set full --clock-control none --import-source on -k regex:'k_trace|k_shade' -s 0 -c 4 \
    -f -o gpurun_out/final_trace python bench.py --spp 2 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_final.log 2>&1
-python scripts/configs_bench.py --skip-sweep > gpurun_out/final_configs_c123.json 2> gpurun_out/final_configs.err
+python tests/configs_bench.py --skip-sweep > gpurun_out/final_configs_c123.json 2> gpurun_out/final_configs.err
 echo done

@@ -1,11 +1,12 @@
 #!/usr/bin/env python
-"""Measures BASELINE.json configs[0..2] (C1 shirley 600x300x32, C2 cornell geometry 1024^2x256x16,
+"""(Lives under tests/ because it uses the oracle as the checker and as the CPU side of the sweep.)
+Measures BASELINE.json configs[0..2] (C1 shirley 600x300x32, C2 cornell geometry 1024^2x256x16,
 C3 synthetic ganesha mesh 1920x1080x256) on one GPU: device throughput at the full size plus image parity
 against the oracle at a reduced size of the same scene; and configs[4] (C5), the intersect_batch sweep
 (rays x spheres / triangles, coherent and incoherent rays) against the oracle's AVX2 leaf kernel / scalar
 Moller-Trumbore on the host.  Writes one JSON document to stdout (progress on stderr).
 
-  python scripts/configs_bench.py [--quick] > gpurun_out/configs.json
+  python tests/configs_bench.py [--quick] > gpurun_out/configs.json
 """
 import argparse
 import json
@@ -15,7 +16,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # tests/ -> repo root
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import path_tracer_ocaml_b200 as P  # noqa: E402
