@@ -148,6 +148,16 @@ __device__ __forceinline__ V3<R> quat_transform(Quat<R> t, V3<R> v) {
   Quat<R> tc = {t.r, neg(t.v)};
   return quat_mul(quat_mul(t, Quat<R>{R(0), v}), tc).v;
 }
+// float path: the shading-frame quaternions always have v.z == 0 (frame_from_normal below), and q v q* for a unit
+// q = (r; a) is v + 2 (r (a x v) + a x (a x v)): 14 instructions instead of the two Hamilton products (~56) the
+// reference spells out (quaternion.ml:25-42).  Same rotation, float rounding only; the float64 validation mode
+// keeps the reference's formula.
+__device__ __forceinline__ V3<float> quat_transform(Quat<float> t, V3<float> v) {
+  const float ax = t.v.x, ay = t.v.y;
+  const float cx = ay * v.z, cy = -ax * v.z, cz = fmaf(ax, v.y, -(ay * v.x));   // c = a x v
+  const float dx = ay * cz, dy = -ax * cz, dz = fmaf(ax, cy, -(ay * cx));        // a x c
+  return {fmaf(2.0f, fmaf(t.r, cx, dx), v.x), fmaf(2.0f, fmaf(t.r, cy, dy), v.y), fmaf(2.0f, fmaf(t.r, cz, dz), v.z)};
+}
 template <class R>
 __device__ __forceinline__ Quat<R> frame_from_normal(V3<R> n) {
   const R eps = sizeof(R) == 4 ? R(1e-7) : R(1e-9);  // shader_space.ml:9 uses 1e-9 (float64)
@@ -1096,9 +1106,9 @@ __global__ void __launch_bounds__(256)
         // Scatter.Diffuse; Pdf.sample = cosine hemisphere (pdf.ml:5-9, shader_space.ml:56-64);
         // diffuse_pd / divisor == 1 exactly, diffuse_pd = 0 iff z = 0 (integrator.ml:48-58)
         R u = r_min(R(ud), Lim<R>::below_one()), sn, cs;
-        R rr = r_sqrt(u);
+        R rr = r_sqrt_fast(u);  // float: MUFU.SQRT (2 ulp); double: exact
         r_sincos2pi(R(vd), &sn, &cs);
-        dir_ss = {rr * cs, rr * sn, r_sqrt(R(1) - u)};
+        dir_ss = {rr * cs, rr * sn, r_sqrt_fast(R(1) - u)};
         alive = dir_ss.z > R(0);
         nattn = {albedo.x * attn0.x, albedo.y * attn0.y, albedo.z * attn0.z};
       } else if (m == PTB_MAT_METAL) {
@@ -1112,7 +1122,7 @@ __global__ void __launch_bounds__(256)
       } else {
         // material.ml:45-57: Dielectric; reflect on TIR or schlick > u, else refract
         R c = r_min(r_max(wi.z, R(0)), R(1));
-        R s = r_sqrt(R(1) - c * c);
+        R s = r_sqrt_fast(R(1) - c * c);
         R ratio = front ? R(1.0 / mat.index) : R(mat.index);
         R q0_ = (R(1) - ratio) / (R(1) + ratio);
         R r0 = q0_ * q0_;
@@ -1122,7 +1132,7 @@ __global__ void __launch_bounds__(256)
         } else {  // Shader_space.refract (shader_space.ml:41-49)
           R cc = r_min(wi.z, R(1));
           V3<R> perp = {(R(0) - wi.x) * ratio, (R(0) - wi.y) * ratio, (cc - wi.z) * ratio};
-          dir_ss = {perp.x, perp.y, perp.z - r_sqrt(r_abs(R(1) - dot(perp, perp)))};
+          dir_ss = {perp.x, perp.y, perp.z - r_sqrt_fast(r_abs(R(1) - dot(perp, perp)))};
         }
         alive = true;
         nattn = attn0;  // Color.white
