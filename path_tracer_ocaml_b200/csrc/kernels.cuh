@@ -1,9 +1,10 @@
 // kernels.cuh — the wavefront pipeline of libptb200: hand-written CUDA for sm_100a.  Product code.
 //
 // Stages (BASELINE.json north_star):
-//   k_raygen   camera rays from the Roberts R2 sequence, evaluated on device in float64 with
-//              un-fused multiplies/adds so the sample stream is bit-identical to the reference
-//              (integrator.ml:98-105, low_discrepancy_sequence.ml:33-36, camera.ml:93-102)
+//   camera_sample  camera rays from the Roberts R2 sequence, evaluated on device in float64 with un-fused
+//              multiplies/adds so the sample stream is bit-identical to the reference (integrator.ml:98-105,
+//              low_discrepancy_sequence.ml:33-36, camera.ml:93-102); called by the bounce-0 k_trace, which
+//              generates its rays in registers, and by k_raygen (test / first-hit entry points only)
 //   k_trace    closest-hit traversal of the 4-wide BVH (nodes + primitives staged in shared memory,
 //              per-thread stack in bank-conflict-free shared memory), ray-sphere and ray-triangle
 //              tests (sphere.ml:35-54 / lib.rs:102-178, triangle.ml:74-98); misses are shaded with
