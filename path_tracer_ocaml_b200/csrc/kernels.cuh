@@ -597,7 +597,9 @@ __device__ __forceinline__ V3<R> tex_eval(const DTex<R> *__restrict__ texs, int 
 template <class R>
 __device__ __forceinline__ V3<R> background(const DScene<R> &sc, V3<R> d) {
   if (sc.bg_kind == PTB_BG_CONSTANT) return {sc.bg0[0], sc.bg0[1], sc.bg0[2]};
-  V3<R> dn = normalize(d);
+  // (every ray of the pipeline has a unit direction — Camera.ray and world_ray produce them — so the float path
+  // skips the reference's re-normalisation; float64 keeps it)
+  V3<R> dn = sizeof(R) == 4 ? d : normalize(d);
   R t = R(0.5) * (dn.y + R(1));
   R s = R(1) - t;
   return {sc.bg0[0] * s + sc.bg1[0] * t, sc.bg0[1] * s + sc.bg1[1] * t, sc.bg0[2] * s + sc.bg1[2] * t};
@@ -647,15 +649,25 @@ __device__ __forceinline__ void seg_close(unsigned seg_base, unsigned seg_fill, 
 struct GenConst {
   int32_t W, spp, npix, pass0, i0, pad;
   double llx, lly, vx, vy, widthf, heightf, alpha0, alpha1;
+  double inv_npix, inv_W;  // (1/d) * (1 - 2^-40): quotient estimates that are never too big (udiv_by below)
   const int32_t *pixel_list;
 };
+// x / d for x < 2^32 without the ~20-instruction integer division sequence: a float64 estimate that is either
+// the quotient or one less, then one fix-up.  r receives the remainder.
+__device__ __forceinline__ unsigned udiv_by(unsigned x, unsigned d, double inv_d, unsigned &r) {
+  unsigned q = (unsigned)__double2uint_rz((double)x * inv_d);
+  r = x - q * d;
+  if (r >= d) ++q, r -= d;
+  return q;
+}
 __device__ __forceinline__ void camera_sample(const GenConst &g, unsigned k, int &pixel, int &offset, double &cx,
                                               double &cy, double &ddx, double &ddy) {
   const unsigned idx = (unsigned)g.i0 + k;  // < npix + batch size < 2^31 (checked on the host)
-  const unsigned q = idx / (unsigned)g.npix;
-  const int i = (int)(idx - q * (unsigned)g.npix);
+  unsigned ri, rx;
+  const unsigned q = udiv_by(idx, (unsigned)g.npix, g.inv_npix, ri);
+  const int i = (int)ri;
   pixel = __ldg(g.pixel_list + i);
-  const int gy = pixel / g.W, gx = pixel - gy * g.W;
+  const int gy = (int)udiv_by((unsigned)pixel, (unsigned)g.W, g.inv_W, rx), gx = (int)rx;
   offset = pixel + (g.pass0 + (int)q) * g.spp;  // integrator.ml:98 (sic: pass * samples_per_pixel)
   const double dx = r2_sample(g.alpha0, offset), dy = r2_sample(g.alpha1, offset);
   cx = __dmul_rn(__dadd_rn((double)gx, dx), g.widthf);                    // integrator.ml:104

@@ -269,6 +269,7 @@ static GenConst make_gen(const RenderConst &rc, const int32_t *pixel_list, int p
   g.W = rc.W, g.spp = rc.spp, g.npix = rc.npix, g.pass0 = pass0, g.i0 = i0;
   g.llx = rc.llx, g.lly = rc.lly, g.vx = rc.vx, g.vy = rc.vy, g.widthf = rc.widthf, g.heightf = rc.heightf;
   g.alpha0 = rc.alpha[0], g.alpha1 = rc.alpha[1];
+  g.inv_npix = (1.0 / (double)rc.npix) * (1.0 - 0x1p-40), g.inv_W = (1.0 / (double)rc.W) * (1.0 - 0x1p-40);
   g.pixel_list = pixel_list;
   return g;
 }
