@@ -259,9 +259,7 @@ def main():
         d2h = int(W * H * 3 * 4)
         e2e_what = ("scene commit (BVH build + table upload) + sharded render + NCCL reduce + resolve + image to "
                     "pinned host memory, wall clock")
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
+    def e2e_step():
         scene.commit(local)  # host->device copy of the step's inputs (the scene tables), incl. BVH build
         if world == 1:
             integ.render(image=host_np)
@@ -270,6 +268,14 @@ def main():
             step(False)
             if rank == 0:
                 host_img.copy_(image, non_blocking=False)
+
+    n_launch_timed = launches[0]
+    e2e_step()  # one untimed pass: the first host-buffer call grows the library's pooled device image buffers
+    launches[0] = n_launch_timed
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
     barrier()
     e2e_s = time.perf_counter() - t0
     e2e_val = paths_per_step * args.steps / e2e_s / 1e6

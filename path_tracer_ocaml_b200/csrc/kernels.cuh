@@ -309,6 +309,13 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_scalar(unsigned saddr, const float *g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_scalar(unsigned saddr, const double *g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(saddr), "l"(g) : "memory");
+}
 template <class R>
 __device__ __forceinline__ void cp_async_vec4(unsigned saddr, const Vec4<R> *g) {
 #pragma unroll
@@ -660,20 +667,26 @@ __device__ __forceinline__ unsigned udiv_by(unsigned x, unsigned d, double inv_d
   if (r >= d) ++q, r -= d;
   return q;
 }
-__device__ __forceinline__ void camera_sample(const GenConst &g, unsigned k, int &pixel, int &offset, double &cx,
-                                              double &cy, double &ddx, double &ddy) {
-  const unsigned idx = (unsigned)g.i0 + k;  // < npix + batch size < 2^31 (checked on the host)
-  unsigned ri, rx;
-  const unsigned q = udiv_by(idx, (unsigned)g.npix, g.inv_npix, ri);
-  const int i = (int)ri;
-  pixel = __ldg(g.pixel_list + i);
+// Sample `idx` of the rank's enumeration is pass idx / npix of pixel pixel_list[idx % npix].  The film position
+// and un-normalized camera-space direction of that sample:
+__device__ __forceinline__ void camera_dir(const GenConst &g, int pixel, int pass, int &offset, double &cx, double &cy,
+                                           double &ddx, double &ddy) {
+  unsigned rx;
   const int gy = (int)udiv_by((unsigned)pixel, (unsigned)g.W, g.inv_W, rx), gx = (int)rx;
-  offset = pixel + (g.pass0 + (int)q) * g.spp;  // integrator.ml:98 (sic: pass * samples_per_pixel)
+  offset = pixel + (g.pass0 + pass) * g.spp;  // integrator.ml:98 (sic: pass * samples_per_pixel)
   const double dx = r2_sample(g.alpha0, offset), dy = r2_sample(g.alpha1, offset);
   cx = __dmul_rn(__dadd_rn((double)gx, dx), g.widthf);                    // integrator.ml:104
   cy = __dsub_rn(1.0, __dmul_rn(__dadd_rn((double)gy, dy), g.heightf));   // integrator.ml:105
   ddx = __dadd_rn(g.llx, __dmul_rn(g.vx, cx));                            // camera.ml:96-97
   ddy = __dadd_rn(g.lly, __dmul_rn(g.vy, cy));
+}
+__device__ __forceinline__ void camera_sample(const GenConst &g, unsigned k, int &pixel, int &offset, double &cx,
+                                              double &cy, double &ddx, double &ddy) {
+  const unsigned idx = (unsigned)g.i0 + k;  // < npix + batch size < 2^31 (checked on the host)
+  unsigned ri;
+  const unsigned q = udiv_by(idx, (unsigned)g.npix, g.inv_npix, ri);
+  pixel = __ldg(g.pixel_list + (int)ri);
+  camera_dir(g, pixel, (int)q, offset, cx, cy, ddx, ddy);
 }
 
 // Stage 1 — camera rays.  One thread per sample of the batch [first, first+n) of this rank's
@@ -688,9 +701,9 @@ __global__ void __launch_bounds__(256) k_raygen(GenConst g, unsigned n, Queue<R>
     if (dbg_cx) dbg_cx[k] = cx;
     if (dbg_cy) dbg_cy[k] = cy;
     V3<R> dir = normalize(V3<R>{R(ddx), R(ddy), R(-1)});
-    out.A[k] = {R(0), R(0), R(0), i2r(pixel, R())};
+    out.A[k] = {R(0), R(0), R(0), R(0)};
     out.B[k] = {dir.x, dir.y, dir.z, i2r(offset, R())};
-    out.C[k] = {R(1), R(1), R(1), R(0)};
+    out.C[k] = {R(1), R(1), R(1), i2r(pixel, R())};
     if (k % SEG == 0) out.seg_count[k / SEG] = (int32_t)(n - k < (unsigned)SEG ? n - k : (unsigned)SEG);  // dense
   }
 }
@@ -711,15 +724,23 @@ __global__ void __launch_bounds__(256) k_raygen(GenConst g, unsigned n, Queue<R>
 // range, open output segments, statistics) sits in a per-warp record.
 //
 // Dynamic shared memory: [scene (SMEM)] [stack: stack_cap x threads x ENTRY] [payload: threads x (Vec4 + R)]
-//                        [warp records: warps x WS_WORDS x 4 B]
+//                        [warp records: warps x WS_WORDS x 4 B] [staging rings: warps x RING x 2 Vec4]
+//
+// Incoming rays never wait on HBM/L2: each warp keeps the next RING entries (origin, direction) of its claimed
+// chunk in flight into its staging ring (cp.async issued one refill ahead), and the payload of a ray goes
+// straight from the queue into the lane's payload slot (cp.async, first read at the lane's flush).
 constexpr int LEAF_MIN = 8;  // lanes holding a leaf before the warp runs the leaf phase (tuned: 6..12 equal, 1: -4 %)
-constexpr unsigned WS_NEXT = 0, WS_END = 1, WS_FETCHED = 2, WS_SEG = 3 /* base,fill x 3 kinds */, WS_WORDS = 12;
+constexpr unsigned WS_NEXT = 0, WS_END = 1, WS_FETCHED = 2, WS_SEG = 3 /* base,fill x 3 kinds */, WS_STAGED = 9,
+                   WS_REM_BASE = 10, WS_REM_CNT = 11 /* whole segments claimed but not opened yet */,
+                   WS_SEEN = 12 /* the cursor at the last claim */, WS_IB = 13, WS_QB = 14 /* GEN: pixel-list index and
+                   pass of entry WS_NEXT */, WS_WORDS = 16;
+constexpr unsigned RING = 32;  // entries of the per-warp staging ring for incoming rays
 
 // dynamic shared memory per thread besides the staged scene: stack + payload slot + share of the warp record
 template <class R>
 __host__ __device__ constexpr size_t trace_smem_per_thread(int stack_cap, bool stack_in_smem) {
   return (size_t)(stack_in_smem ? stack_cap : PTB_STACK_HOT) * 2u * sizeof(R) + sizeof(Vec4<R>) + sizeof(R) +
-         (WS_WORDS * 4u + 31u) / 32u;
+         (WS_WORDS * 4u + 31u) / 32u + RING * 2u * sizeof(Vec4<R>) / 32u;
 }
 
 // GEN: bounce 0 — the rays are the camera samples [0, gen_n) of the batch, generated in registers
@@ -792,8 +813,14 @@ __global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, SM
   const unsigned pay_v = pay_base + (unsigned)tid * (unsigned)sizeof(Vec4<R>);
   const unsigned pay_r = pay_base + blockDim.x * (unsigned)sizeof(Vec4<R>) + (unsigned)tid * (unsigned)sizeof(R);
   const unsigned ws = pay_base + blockDim.x * (unsigned)(sizeof(Vec4<R>) + sizeof(R)) + ((unsigned)tid >> 5) * (WS_WORDS * 4u);
-  if (lane < WS_WORDS) sts_i32(ws + lane * 4u, (lane >= WS_SEG && ((lane - WS_SEG) & 1u) == 0u) ? (int)NO_SEG : 0);
+  if (lane < WS_WORDS)
+    sts_i32(ws + lane * 4u, (lane >= WS_SEG && lane < WS_STAGED && ((lane - WS_SEG) & 1u) == 0u) ? (int)NO_SEG : 0);
   __syncwarp();
+  constexpr unsigned VB = (unsigned)sizeof(Vec4<R>);
+  // staging ring of this warp: RING origins, then RING directions (entry i of the queue sits in slot i % RING)
+  const unsigned ring_a = pay_base + blockDim.x * (unsigned)(sizeof(Vec4<R>) + sizeof(R)) + (blockDim.x >> 5) * (WS_WORDS * 4u) +
+                          ((unsigned)tid >> 5) * (2u * RING * VB);
+  const unsigned ring_b = ring_a + RING * VB;
 
   Lane<R> L;
   L.cur = TRAV_IDLE, L.sp = sp0, L.best = -1, L.tbest = R(0);
@@ -816,6 +843,7 @@ __global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, SM
         const unsigned lt_mask = (1u << lane) - 1u;
         int kind = -1;
         Vec4<R> pv = {R(0), R(0), R(0), R(0)};  // (attenuation, pixel)
+        if (!GEN) cp_async_wait_all();  // this lane's payload copy (issued at its refill, long since complete)
         if (done) {
           pv = lds_vec4(pay_v, R());
           if (L.best < 0) {
@@ -867,79 +895,143 @@ __global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, SM
       }
       if (done) L.cur = TRAV_IDLE;
     }
-    // ---------------- refill idle lanes from the queue (one parallel round trip) ----------------
+    // ---------------- refill idle lanes --------------------------------------------------------
+    // The warp works through a CHUNK [next, end) of contiguous queue entries.  Chunks come from claims of 1, 2 or 4
+    // whole segments (guided: big claims while much of the queue is left, single segments towards its end; parts
+    // of a segment when the launch is small); a claim's run of full segments is one chunk.  What the NEXT refill
+    // will take is already in flight into the staging ring, and a new chunk is opened as soon as the old one runs
+    // out, not when its entries are needed, so that a refill normally finds everything in shared memory.
     const unsigned idle = __ballot_sync(0xffffffffu, L.cur == TRAV_IDLE);
     if (more && idle) {
-      unsigned chunk_next = (unsigned)lds_i32(ws + WS_NEXT * 4u), chunk_end = (unsigned)lds_i32(ws + WS_END * 4u);
+      unsigned next = (unsigned)lds_i32(ws + WS_NEXT * 4u), end = (unsigned)lds_i32(ws + WS_END * 4u);
+      unsigned staged = (unsigned)lds_i32(ws + WS_STAGED * 4u);  // [next, staged) is in, or on its way into, the ring
+      unsigned ib = 0, qb = 0;
+      if (GEN) ib = (unsigned)lds_i32(ws + WS_IB * 4u), qb = (unsigned)lds_i32(ws + WS_QB * 4u);
       __syncwarp();
-      if (chunk_next >= chunk_end) {  // claim the next unit (segment or part of one) of the input queue
-        const unsigned claim = (unsigned)SEG >> claim_shift;
-        const unsigned nunits = nseg << claim_shift;
-        unsigned u = 0, c = 0;
-        if (lane == 0) {
-          u = atomicAdd(cursor, 1u);
-          if (u < nunits) {
+      unsigned idle_left = idle;
+      for (;;) {
+        if (next < end) {  // hand entries [next, next + take) to the idle lanes
+          cp_async_wait_all();
+          __syncwarp();
+          const unsigned want = (unsigned)__popc(idle_left), avail = end - next;
+          const unsigned take = want < avail ? want : avail;
+          const unsigned rank = (unsigned)__popc(idle_left & ((1u << lane) - 1u));
+          const bool mine = ((idle_left >> lane) & 1u) != 0u && rank < take;
+          if (mine) {
+            ray_i = next + rank;
             if (GEN) {
-              const unsigned s0 = (u >> claim_shift) * (unsigned)SEG;
-              c = gen_n - s0 < (unsigned)SEG ? gen_n - s0 : (unsigned)SEG;
-            } else {
-              c = (unsigned)rays.seg_count[u >> claim_shift];
-            }
-          }
-        }
-        u = __shfl_sync(0xffffffffu, u, 0);
-        c = __shfl_sync(0xffffffffu, c, 0);
-        const unsigned off = (u & ((1u << claim_shift) - 1u)) * claim;  // offset of the unit inside its segment
-        const unsigned lim = c < off + claim ? c : off + claim;         // valid entries end here
-        chunk_next = (u >> claim_shift) * SEG + off;
-        chunk_end = lim > off ? (u >> claim_shift) * SEG + lim : chunk_next;
-        if (u >= nunits) {
-          more = false;
-          chunk_next = chunk_end = 0;
-        }
-      }
-      if (more) {
-        const unsigned want = (unsigned)__popc(idle);
-        const unsigned avail = chunk_end - chunk_next;
-        const unsigned take = want < avail ? want : avail;
-        const unsigned rank = (unsigned)__popc(idle & ((1u << lane) - 1u));
-        if (L.cur == TRAV_IDLE && rank < take) {
-          ray_i = chunk_next + rank;
-          if (GEN) {
-            int pixel, offset;
-            double cx, cy, ddx, ddy;
-            camera_sample(gen, ray_i, pixel, offset, cx, cy, ddx, ddy);
-            const V3<R> dir = normalize(V3<R>{R(ddx), R(ddy), R(-1)});
-            const Vec4<R> pv = {R(1), R(1), R(1), i2r(pixel, R())};
-            sts_vec4(pay_v, pv);
-            sts_r(pay_r, i2r(offset, R()));
-            lane_init<R>(L, V3<R>{R(0), R(0), R(0)}, dir, R(0), Lim<R>::tmax(), sp0);
-          } else {
-            const Vec4<R> A = rays.A[ray_i], B = rays.B[ray_i];
-            if (MODE == 0) {
-              const Vec4<R> C = rays.C[ray_i];
-              // park the payload: (attenuation, pixel) and the R2 offset
-              const Vec4<R> pv = {C.x, C.y, C.z, A.w};
+              unsigned i = ib + rank, q = qb;
+              while (i >= (unsigned)gen.npix) i -= (unsigned)gen.npix, ++q;
+              const int pixel = lds_i32(ring_a + (ray_i % RING) * 4u);
+              int offset;
+              double cx, cy, ddx, ddy;
+              camera_dir(gen, pixel, (int)q, offset, cx, cy, ddx, ddy);
+              const V3<R> dir = normalize(V3<R>{R(ddx), R(ddy), R(-1)});
+              const Vec4<R> pv = {R(1), R(1), R(1), i2r(pixel, R())};
               sts_vec4(pay_v, pv);
-              sts_r(pay_r, B.w);
+              sts_r(pay_r, i2r(offset, R()));
+              lane_init<R>(L, V3<R>{R(0), R(0), R(0)}, dir, R(0), Lim<R>::tmax(), sp0);
+            } else {
+              const Vec4<R> A = lds_vec4(ring_a + (ray_i % RING) * VB, R()), B = lds_vec4(ring_b + (ray_i % RING) * VB, R());
+              if (MODE == 0) {
+                // the payload, (attenuation, pixel) and the R2 offset, goes from the queue straight into this lane's slot
+                cp_async_vec4<R>(pay_v, rays.C + ray_i);
+                sts_r(pay_r, B.w);
+              }
+              lane_init<R>(L, V3<R>{A.x, A.y, A.z}, V3<R>{B.x, B.y, B.z}, (MODE == 0) ? R(0) : tmin_arg,
+                           (MODE == 0) ? Lim<R>::tmax() : tmax_arg, sp0);
             }
-            lane_init<R>(L, V3<R>{A.x, A.y, A.z}, V3<R>{B.x, B.y, B.z}, (MODE == 0) ? R(0) : tmin_arg,
-                         (MODE == 0) ? Lim<R>::tmax() : tmax_arg, sp0);
+          }
+          idle_left &= ~__ballot_sync(0xffffffffu, mine);  // (also orders the ring reads before the next copies into it)
+          next += take;
+          if (GEN) {
+            ib += take;
+            while (ib >= (unsigned)gen.npix) ib -= (unsigned)gen.npix, ++qb;
           }
         }
-        chunk_next += take;
-        if (lane == 0 && MODE == 0) sts_i32(ws + WS_FETCHED * 4u, lds_i32(ws + WS_FETCHED * 4u) + (int)take);
-        if (!GEN) {
-          // the entries the NEXT refill will take: start them on their way from HBM into L2 now
-          const unsigned pf = chunk_next + lane;
-          if (pf < chunk_end) {
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(rays.A + pf));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(rays.B + pf));
-            if (MODE == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(rays.C + pf));
+        if (next >= end) {  // open the next chunk
+          unsigned rem_base = (unsigned)lds_i32(ws + WS_REM_BASE * 4u), rem_cnt = (unsigned)lds_i32(ws + WS_REM_CNT * 4u);
+          __syncwarp();
+          if (rem_cnt == 0u) {  // nothing left of the last claim: claim more of the input queue
+            const unsigned nunits = nseg << claim_shift;
+            unsigned g = 1u;
+            if (claim_shift == 0u) {
+              const unsigned seen = (unsigned)lds_i32(ws + WS_SEEN * 4u), nwarps = gridDim.x * (blockDim.x >> 5);
+              const unsigned left = seen < nunits ? nunits - seen : 0u;
+              g = left > 16u * nwarps ? 4u : (left > 8u * nwarps ? 2u : 1u);
+            }
+            unsigned u = 0;
+            if (lane == 0) u = atomicAdd(cursor, g);
+            u = __shfl_sync(0xffffffffu, u, 0);
+            if (u >= nunits) {
+              more = false;
+              next = end = staged = 0;
+              break;
+            }
+            if (claim_shift != 0u) {  // small launch: a unit is a part of one segment
+              const unsigned claim = (unsigned)SEG >> claim_shift, sgm = u >> claim_shift;
+              unsigned c = 0;
+              if (GEN) {
+                c = gen_n - sgm * (unsigned)SEG < (unsigned)SEG ? gen_n - sgm * (unsigned)SEG : (unsigned)SEG;
+              } else {
+                if (lane == 0) c = (unsigned)rays.seg_count[sgm];
+                c = __shfl_sync(0xffffffffu, c, 0);
+              }
+              const unsigned off = (u & ((1u << claim_shift) - 1u)) * claim;  // offset of the unit inside its segment
+              const unsigned lim = c < off + claim ? c : off + claim;         // valid entries end here
+              next = sgm * SEG + off;
+              end = lim > off ? sgm * SEG + lim : next;
+            } else {
+              rem_base = u, rem_cnt = nunits - u < g ? nunits - u : g;
+              if (lane == 0) sts_i32(ws + WS_SEEN * 4u, (int)u);
+            }
           }
+          if (rem_cnt != 0u) {  // the run of full segments at the head of the remainder, plus the first partial one
+            unsigned c = (unsigned)SEG;
+            if (lane < rem_cnt) {
+              if (GEN) {
+                const unsigned s0 = (rem_base + lane) * (unsigned)SEG;
+                c = gen_n - s0 < (unsigned)SEG ? gen_n - s0 : (unsigned)SEG;
+              } else {
+                c = (unsigned)rays.seg_count[rem_base + lane];
+              }
+            }
+            const unsigned partial = __ballot_sync(0xffffffffu, c != (unsigned)SEG);
+            const unsigned first_p = partial ? (unsigned)__ffs((int)partial) - 1u : rem_cnt;
+            const unsigned nsegs = first_p < rem_cnt ? first_p + 1u : rem_cnt;
+            const unsigned last_c = __shfl_sync(0xffffffffu, c, nsegs - 1u);
+            next = rem_base * SEG;
+            end = (rem_base + nsegs - 1u) * SEG + last_c;
+            rem_base += nsegs, rem_cnt -= nsegs;
+            if (lane == 0) sts_i32(ws + WS_REM_BASE * 4u, (int)rem_base), sts_i32(ws + WS_REM_CNT * 4u, (int)rem_cnt);
+          }
+          if (lane == 0 && MODE == 0) sts_i32(ws + WS_FETCHED * 4u, lds_i32(ws + WS_FETCHED * 4u) + (int)(end - next));
+          staged = next;
+          if (GEN) qb = udiv_by((unsigned)gen.i0 + next, (unsigned)gen.npix, gen.inv_npix, ib);
+          if (next >= end) continue;  // an empty unit (the tail of a partly filled segment)
         }
+        {  // keep the next RING entries of the chunk in flight
+          const unsigned upto = end - next > RING ? next + RING : end;
+          const unsigned e = staged + lane;
+          if (e < upto) {
+            if (GEN) {
+              unsigned i = ib + (e - next);
+              while (i >= (unsigned)gen.npix) i -= (unsigned)gen.npix;
+              cp_async_scalar(ring_a + (e % RING) * 4u, reinterpret_cast<const float *>(gen.pixel_list + i));
+            } else {
+              cp_async_vec4<R>(ring_a + (e % RING) * VB, rays.A + e);
+              cp_async_vec4<R>(ring_b + (e % RING) * VB, rays.B + e);
+            }
+          }
+          if (staged < upto) staged = upto;
+        }
+        if (idle_left == 0u) break;
       }
-      if (lane == 0) sts_i32(ws + WS_NEXT * 4u, (int)chunk_next), sts_i32(ws + WS_END * 4u, (int)chunk_end);
+      if (lane == 0) {
+        sts_i32(ws + WS_NEXT * 4u, (int)next), sts_i32(ws + WS_END * 4u, (int)end);
+        sts_i32(ws + WS_STAGED * 4u, (int)staged);
+        if (GEN) sts_i32(ws + WS_IB * 4u, (int)ib), sts_i32(ws + WS_QB * 4u, (int)qb);
+      }
       __syncwarp();
     }
     const unsigned active = __ballot_sync(0xffffffffu, L.cur > TRAV_DONE);
@@ -1156,9 +1248,9 @@ __global__ void __launch_bounds__(256)
     }
     const unsigned dst = seg_append(alive, ob, of, nseg_out, out.seg_count, lane, lt_mask);
     if (alive) {
-      out.A[dst] = {no.x, no.y, no.z, A.w};
+      out.A[dst] = {no.x, no.y, no.z, R(0)};
       out.B[dst] = {nd.x, nd.y, nd.z, B.w};
-      out.C[dst] = {nattn.x, nattn.y, nattn.z, R(0)};
+      out.C[dst] = {nattn.x, nattn.y, nattn.z, A.w};
     }
    }
   }

@@ -1194,8 +1194,8 @@ int ptb_raygen(const ptb_params *p, int64_t first, int64_t n, int32_t *pixel, in
     k_raygen<float><<<(unsigned)((n + 255) / 256), 256>>>(make_gen(rcst, tmp.pixel_list, pass0, i0), (unsigned)n, q, d_cx, d_cy);
   }
   CK(cudaGetLastError());
-  std::vector<Vec4<float>> A(nn), B(nn);
-  CK(cudaMemcpy(A.data(), q.A, (size_t)n * 16, cudaMemcpyDeviceToHost));
+  std::vector<Vec4<float>> A(nn), B(nn);  // A: the entry's C (attenuation, pixel)
+  CK(cudaMemcpy(A.data(), q.C, (size_t)n * 16, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(B.data(), q.B, (size_t)n * 16, cudaMemcpyDeviceToHost));
   if (cx) CK(cudaMemcpy(cx, d_cx, (size_t)n * 8, cudaMemcpyDeviceToHost));
   if (cy) CK(cudaMemcpy(cy, d_cy, (size_t)n * 8, cudaMemcpyDeviceToHost));
