@@ -35,11 +35,16 @@ struct alignas(16) Node4 {
 static_assert(sizeof(Node4<float>) == 112, "Node4<float> must be 7 x 16 bytes");
 static_assert(sizeof(Node4<double>) == 208, "Node4<double> must be 13 x 16 bytes");
 
-struct DMat {
+struct alignas(16) DMat {
   int32_t kind;
   int32_t tex;
   double index;
+  // the kind of texture `tex` and, when it is a solid one, its colour: the float path shades without the
+  // dependent load of the texture record
+  int32_t tex_kind;
+  float rgb[3];
 };
+static_assert(sizeof(DMat) == 32, "DMat is read as two 16-byte words");
 template <class R>
 struct DTex {
   int32_t kind, w, h, even, odd, pad;

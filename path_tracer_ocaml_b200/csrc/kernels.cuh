@@ -1071,14 +1071,20 @@ __global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, SM
 
 // Stage 4 — material scatter.  Work item = one warp-sized chunk of ONE material's hit queue, so the
 // material switch below is warp-uniform.
+constexpr unsigned SHADE_NBUF = 3;  // staging buffers per thread: SHADE_NBUF - 1 items in flight while one is shaded
+template <class R>
+__host__ __device__ constexpr size_t shade_smem_bytes(unsigned block) {
+  return (size_t)SHADE_NBUF * (3u * block * sizeof(Vec4<R>) + (block / 32u) * 4u);
+}
 template <class R>
 __global__ void __launch_bounds__(256)
     k_shade(DScene<R> sc, RenderConst rc, int bounce, Queue<R> q0, unsigned q_slots,
-            const unsigned *__restrict__ nseg_mat, Queue<R> out, unsigned *__restrict__ nseg_out) {
+            unsigned *__restrict__ nseg_mat, Queue<R> out, unsigned *__restrict__ nseg_out) {
   // Software pipeline over the warp's work items (one item = 32 entries of one segment of one material's hit
-  // queue): while item k is shaded, the 48 B entries of item k+1 are already in flight into shared memory
-  // (cp.async, each lane copies and later reads only its own entry) and the segment fill count of item k+2 is
-  // being loaded, so the queue's HBM latency is off the critical path of every iteration.
+  // queue): while item k is shaded, the 48 B entries of items k+1 .. k+SHADE_NBUF-1 and the fill counts of their
+  // segments are in flight into shared memory (cp.async: no register and no scoreboard is tied up, each lane
+  // copies and later reads only its own entry), enough bytes in flight per SM to keep HBM busy.  The copy does
+  // not wait for the fill count: entries past it are allocated queue slots that are simply not used.
   extern __shared__ __align__(16) unsigned char shade_smem[];
   const unsigned lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
@@ -1089,9 +1095,10 @@ __global__ void __launch_bounds__(256)
   const double alpha_u = rc.alpha[j], alpha_v = rc.alpha[j + 1];
   unsigned ob = NO_SEG, of = 0;  // warp-uniform: this warp's open segment in the output ray queue
   constexpr unsigned VB = (unsigned)sizeof(Vec4<R>);
-  // staging slots: [buffer 0/1][A,B,C][thread]
+  // staging slots: [buffer][A,B,C][thread], then [warp][buffer] fill counts
   const unsigned sbase = (unsigned)__cvta_generic_to_shared(shade_smem);
   const unsigned slot0 = sbase + threadIdx.x * VB, bufsz = 3u * blockDim.x * VB, arr = blockDim.x * VB;
+  const unsigned cnt0 = sbase + SHADE_NBUF * bufsz + (threadIdx.x >> 5) * (SHADE_NBUF * 4u);
   // item -> (material, segment, first entry)
   auto decode = [&](unsigned w, int &m, unsigned &seg, unsigned &i0) {
     seg = w / (SEG / 32);
@@ -1100,44 +1107,68 @@ __global__ void __launch_bounds__(256)
     else if (seg < c0 + c1) m = 1, seg -= c0;
     else m = 2, seg -= c0 + c1;
   };
-  auto fill_of = [&](unsigned w) -> unsigned {  // valid entries of the item's segment
+  auto prefetch = [&](unsigned w, unsigned buf) {
     int m;
     unsigned seg, i0;
     decode(w, m, seg, i0);
-    return (unsigned)__ldg(q0.seg_count + (unsigned)m * (q_slots / SEG) + seg);
+    const unsigned i = (unsigned)m * q_slots + seg * SEG + i0 + lane;  // entry in the joint allocation
+    const unsigned dst = slot0 + buf * bufsz;
+    cp_async_vec4<R>(dst, q0.A + i);
+    cp_async_vec4<R>(dst + arr, q0.B + i);
+    cp_async_vec4<R>(dst + 2u * arr, q0.C + i);
+    if (lane == 0)
+      cp_async_scalar(cnt0 + buf * 4u, reinterpret_cast<const float *>(q0.seg_count + (unsigned)m * (q_slots / SEG) + seg));
   };
-  auto prefetch = [&](unsigned w, unsigned nm, unsigned buf) {
-    int m;
-    unsigned seg, i0;
-    decode(w, m, seg, i0);
-    if (i0 + lane < nm) {
-      const unsigned i = (unsigned)m * q_slots + seg * SEG + i0 + lane;  // entry in the joint allocation
-      const unsigned dst = slot0 + buf * bufsz;
-      cp_async_vec4<R>(dst, q0.A + i);
-      cp_async_vec4<R>(dst + arr, q0.B + i);
-      cp_async_vec4<R>(dst + 2u * arr, q0.C + i);
+  // Items are handed out dynamically, a few at a time (nseg_mat[3] is the launch's cursor): the SMs do not all get
+  // the same share of the memory system (GPCs differ in size), and with a static split the slowest ones set
+  // the kernel's time.  The claim for the range after next is issued when a range is opened, so its latency is
+  // covered by the items of a whole range.
+  constexpr unsigned NONE = 0xffffffffu;
+  unsigned *cursor = nseg_mat + 3;
+  const unsigned per_claim = total / (warps * 4u) >= 8u ? 8u : (total / (warps * 4u) >= 1u ? total / (warps * 4u) : 1u);
+  unsigned range_next = 0, range_end = 0, pending = 0;
+  bool claims_left = true;
+  if (lane == 0) pending = atomicAdd(cursor, per_claim);
+  auto next_item = [&]() -> unsigned {  // warp-uniform
+    if (range_next == range_end) {
+      if (!claims_left) return NONE;
+      const unsigned base = __shfl_sync(0xffffffffu, pending, 0);
+      if (base >= total) {
+        claims_left = false;
+        return NONE;
+      }
+      range_next = base, range_end = total - base < per_claim ? total : base + per_claim;
+      if (lane == 0) pending = atomicAdd(cursor, per_claim);
     }
+    return range_next++;
   };
-  unsigned w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  unsigned nm_cur = 0, nm_next = 0, buf = 0;
-  if (w < total) {
-    nm_cur = fill_of(w);
-    prefetch(w, nm_cur, 0u);
-    if (w + warps < total) nm_next = fill_of(w + warps);
-  }
-  cp_async_commit();
-  for (; w < total; w += warps) {
-    const unsigned w1 = w + warps, w2 = w1 + warps;
-    unsigned nm_next2 = 0;
-    if (w2 < total) nm_next2 = fill_of(w2);         // in flight during this iteration
-    if (w1 < total) prefetch(w1, nm_next, buf ^ 1u);  // in flight during this iteration
+  unsigned ids[SHADE_NBUF - 1];  // the items in flight, ids[0] is shaded next
+#pragma unroll
+  for (unsigned k = 0; k + 1 < SHADE_NBUF; ++k) {
+    ids[k] = next_item();
+    if (ids[k] != NONE) prefetch(ids[k], k);
     cp_async_commit();
-    cp_async_wait<1>();  // item w has landed
+  }
+  unsigned buf = 0;
+  while (ids[0] != NONE) {
+    __syncwarp();  // every lane is done with the buffer of the item before, which is filled next
+    const unsigned w = ids[0];
+#pragma unroll
+    for (unsigned k = 0; k + 2 < SHADE_NBUF; ++k) ids[k] = ids[k + 1];
+    {
+      const unsigned wn = next_item();
+      ids[SHADE_NBUF - 2] = wn;
+      if (wn != NONE) prefetch(wn, buf == 0u ? SHADE_NBUF - 1u : buf - 1u);
+    }
+    cp_async_commit();
+    cp_async_wait<SHADE_NBUF - 1>();  // item w has landed
+    __syncwarp();        // (lane 0 copied the count for the warp)
     int m;
     unsigned seg, i0;
     decode(w, m, seg, i0);
-    const unsigned nm = nm_cur, cbuf = buf;
-    nm_cur = nm_next, nm_next = nm_next2, buf ^= 1u;
+    const unsigned cbuf = buf;
+    const unsigned nm = (unsigned)lds_i32(cnt0 + cbuf * 4u);  // valid entries of the item's segment
+    buf = buf + 1u == SHADE_NBUF ? 0u : buf + 1u;
     if (i0 >= nm) continue;
    {
     const bool valid = i0 + lane < nm;
@@ -1155,15 +1186,31 @@ __global__ void __launch_bounds__(256)
       const int best = r2i(C.w);
       const int slot = best & 0x3FFFFFFF;
       const bool is_tri = (best >> 30) & 1;
+      // table look-ups first (dependent loads: slot -> material row -> material), the sample arithmetic in between
+      Vec4<R> v0 = {R(0), R(0), R(0), R(0)}, e1 = v0, e2 = v0, s = v0;
+      int mrow;
+      if (!is_tri) {
+        s = ldg_vec4(sc.spheres + slot);
+        mrow = __ldg(sc.sphere_mat + slot);
+      } else {
+        v0 = ldg_vec4(sc.tris + 3 * (size_t)slot), e1 = ldg_vec4(sc.tris + 3 * (size_t)slot + 1);
+        e2 = ldg_vec4(sc.tris + 3 * (size_t)slot + 2);
+        mrow = __ldg(sc.tri_mat + slot);
+      }
+      const double ud = r2_sample(alpha_u, offset), vd = r2_sample(alpha_v, offset);
+      DMat mat;
+      {
+        const int4 m0 = __ldg(reinterpret_cast<const int4 *>(sc.mats + mrow)),
+                   m1 = __ldg(reinterpret_cast<const int4 *>(sc.mats + mrow) + 1);
+        mat.kind = m0.x, mat.tex = m0.y, mat.index = __hiloint2double(m0.w, m0.z);
+        mat.tex_kind = m1.x, mat.rgb[0] = __int_as_float(m1.y), mat.rgb[1] = __int_as_float(m1.z), mat.rgb[2] = __int_as_float(m1.w);
+      }
       // geometric normal (sphere.ml:21 / triangle.ml:18-23)
       V3<R> n;
-      Vec4<R> v0 = {R(0), R(0), R(0), R(0)}, e1 = v0, e2 = v0;
       if (!is_tri) {
-        const Vec4<R> s = sc.spheres[slot];
         n = normalize(V3<R>{p.x - s.x, p.y - s.y, p.z - s.z});
         if (sizeof(R) == 4) p = {r_fma(n.x, s.w, s.x), r_fma(n.y, s.w, s.y), r_fma(n.z, s.w, s.z)};
       } else {
-        v0 = sc.tris[3 * (size_t)slot], e1 = sc.tris[3 * (size_t)slot + 1], e2 = sc.tris[3 * (size_t)slot + 2];
         n = normalize(cross(V3<R>{e1.x, e1.y, e1.z}, V3<R>{e2.x, e2.y, e2.z}));
       }
       const bool front = dot(d, n) < R(0);  // sphere.ml:60 / triangle.ml:56
@@ -1171,13 +1218,12 @@ __global__ void __launch_bounds__(256)
       const Quat<R> frame = frame_from_normal(n);              // Shader_space.create
       const V3<R> wi = quat_transform(frame, neg(d));           // Shader_space.omega_i
       const Quat<R> frame_inv = {frame.r, neg(frame.v)};
-      const int mrow = is_tri ? sc.tri_mat[slot] : sc.sphere_mat[slot];
-      const DMat mat = sc.mats[mrow];
-      const double ud = r2_sample(alpha_u, offset), vd = r2_sample(alpha_v, offset);
       V3<R> albedo = {R(1), R(1), R(1)};
       if (m != PTB_MAT_DIELECTRIC) {
-        const DTex<R> T = sc.texs[mat.tex];
-        if (T.kind == PTB_TEX_SOLID) {
+        if (sizeof(R) == 4 && mat.tex_kind == PTB_TEX_SOLID) {
+          albedo = {R(mat.rgb[0]), R(mat.rgb[1]), R(mat.rgb[2])};
+        } else if (sizeof(R) == 8 && mat.tex_kind == PTB_TEX_SOLID) {
+          const DTex<R> T = sc.texs[mat.tex];
           albedo = {T.rgb[0], T.rgb[1], T.rgb[2]};
         } else {
           R tu, tv;

@@ -2,6 +2,7 @@
 // Product code: nothing from oracle/, no CPU fallback (every entry point needs a CUDA device).
 #include <algorithm>
 #include <chrono>
+#include <cstdio>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -422,7 +423,7 @@ static int render_impl(ptb_scene *s, const ptb_params &p, R *d_sums, cudaStream_
   CK(cudaMemsetAsync(ctl, 0, sizeof(Ctl), st));
   CK(cudaEventRecord(e0, st));
   uint64_t launches = 0;
-  const size_t shade_smem = 2 * 3 * 256 * sizeof(Vec4<R>);  // two staging buffers of (A, B, C) per thread
+  const size_t shade_smem = shade_smem_bytes<R>(256);  // staging buffers of (A, B, C) per thread + fill counts
   CK(cudaFuncSetAttribute(k_shade<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shade_smem));
   int shade_per_sm = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&shade_per_sm, k_shade<R>, 256, shade_smem));
@@ -478,6 +479,16 @@ static int render_impl(ptb_scene *s, const ptb_params &p, R *d_sums, cudaStream_
       tr += m;
     }
     stats->ms_trace = tr;
+    if (std::getenv("PTB_TIMING")) {  // per-launch device times: trace of bounce b, and the shade that follows it
+      const size_t per_batch = 2 * (size_t)p.max_bounces;
+      for (size_t i = 0; i + 1 < tev.size(); i += 2) {
+        float t = 0, sh = 0;
+        cudaEventElapsedTime(&t, tev[i], tev[i + 1]);
+        if (i + 2 < tev.size() && (i + 2) % per_batch != 0) cudaEventElapsedTime(&sh, tev[i + 1], tev[i + 2]);
+        std::fprintf(stderr, "[ptb timing] batch %zu bounce %zu: trace %.3f ms, shade %.3f ms (rays at this bounce, all batches: %llu)\n",
+                     i / per_batch, (i % per_batch) / 2, t, sh, (unsigned long long)host.rays_by_bounce[(i % per_batch) / 2]);
+      }
+    }
   }
   for (cudaEvent_t e : tev) cudaEventDestroy(e);
   cudaEventDestroy(e0);
@@ -528,6 +539,17 @@ static int render_host_impl(ptb_scene *s, const ptb_params &p, double *image, pt
     }
   }
   return rc;
+}
+
+static DMat make_dmat(const HostScene &h, size_t i) {
+  DMat m;
+  m.kind = h.mat[i].kind, m.tex = h.mat[i].texture, m.index = h.mat[i].index;
+  m.tex_kind = PTB_TEX_SOLID, m.rgb[0] = m.rgb[1] = m.rgb[2] = 1.0f;
+  if (m.tex >= 0 && (size_t)m.tex < h.tex.size()) {
+    const ptb_texture &x = h.tex[m.tex];
+    m.tex_kind = x.kind, m.rgb[0] = (float)x.rgb[0], m.rgb[1] = (float)x.rgb[1], m.rgb[2] = (float)x.rgb[2];
+  }
+  return m;
 }
 
 static int new_device_state(ptb_scene *s, int device) {
@@ -741,7 +763,7 @@ static int gpu_build_mesh(ptb_scene *s) {
     texs[i] = {x.kind, x.width, x.height, x.even, x.odd, 0, {(float)x.rgb[0], (float)x.rgb[1], (float)x.rgb[2]}};
   }
   std::vector<DMat> mats(h.mat.size());
-  for (size_t i = 0; i < mats.size(); ++i) mats[i] = {h.mat[i].kind, h.mat[i].texture, h.mat[i].index};
+  for (size_t i = 0; i < mats.size(); ++i) mats[i] = make_dmat(h, i);
   G(upload(&t.texs, texs)) G(upload(&d->mats, mats))
   cudaError_t e = cudaDeviceSynchronize();
   cleanup();
@@ -834,7 +856,7 @@ static int upload_scene(ptb_scene *s, int32_t device) {
   for (size_t k = 0; k < smat.size(); ++k) smat[k] = h.smat[s->bvh.sphere_order[k]];
   for (size_t k = 0; k < tmat.size(); ++k) tmat[k] = h.tmat[s->bvh.tri_order[k]];
   std::vector<DMat> mats(h.mat.size());
-  for (size_t i = 0; i < mats.size(); ++i) mats[i] = {h.mat[i].kind, h.mat[i].texture, h.mat[i].index};
+  for (size_t i = 0; i < mats.size(); ++i) mats[i] = make_dmat(h, i);
   if ((rc = upload(&d->sphere_id, s->bvh.sphere_order))) return rc;
   if ((rc = upload(&d->tri_id, s->bvh.tri_order))) return rc;
   if ((rc = upload(&d->sphere_mat, smat))) return rc;

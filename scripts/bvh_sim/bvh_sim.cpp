@@ -62,6 +62,7 @@ static int SPEC = 0;   // 1: speculative traversal: a lane parks ONE leaf and ke
 static int DEFER = 0;  // 1: flush work runs on full warps of parked results (cost C_FLUSH per 32 rays) + C_PARK per event
 static int C_PARK = 25;
 static int ONE = 0;  // 1: the leaf phase tests ONE sphere per iteration (multi-sphere leaves stay pending)
+static int DOUBLE = 0;  // 1: two node steps per loop iteration
 static int LEAF_T = 1; // leaf phase runs when >= LEAF_T lanes hold a leaf, or no lane can do anything else
 static int C_NODE = 93, C_SPH = 36, C_LEAF0 = 12, C_POP0 = 8, C_POPIT = 6, C_LOOP = 14, C_FLUSH = 90, C_REFILL = 85;
 
@@ -91,10 +92,10 @@ static void init_lane(Lane &L, const Ray &r) {
   L.active = true;
 }
 
-// one if-if iteration for a warp; returns cost
-static void warp_iter(Lane *W, Counts &C) {
-  bool any_node = false, any_leaf = false, any_pop = false;
-  int nl_node = 0, nl_leaf = 0;
+// node step of every lane that is at an inner node; returns the number of lanes that took it
+static int node_step(Lane *W, Counts &C) {
+  bool any_node = false;
+  int nl_node = 0;
   // node phase
   for (int l = 0; l < 32; ++l) {
     Lane &L = W[l];
@@ -133,6 +134,48 @@ static void warp_iter(Lane *W, Counts &C) {
       for (int k = 3; k >= 1; --k)
         if (tn[order[k]] < INFINITY) L.stk.push_back({ch[order[k]], tn[order[k]]});
     }
+  }
+  return nl_node;
+}
+// pop step of every lane in POP state; returns the longest pop loop (0: no lane popped)
+static int pop_step(Lane *W, Counts &C) {
+  int max_pop = 0;
+  for (int l = 0; l < 32; ++l) {
+    Lane &L = W[l];
+    if (!L.active || L.cur != POP) continue;
+    int it = 0;
+    for (;;) {
+      ++it;
+      if (L.stk.empty()) {
+        L.cur = DONE;
+        L.active = false;
+        break;
+      }
+      auto e = L.stk.back();
+      L.stk.pop_back();
+      C.pop++;
+      if (e.second <= L.tbest) {
+        L.cur = e.first;
+        break;
+      }
+    }
+    max_pop = std::max(max_pop, it);
+  }
+  return max_pop;
+}
+
+// one if-if iteration for a warp; returns cost
+static void warp_iter(Lane *W, Counts &C) {
+  bool any_node = false, any_leaf = false, any_pop = false;
+  int nl_node = 0, nl_leaf = 0;
+  nl_node = node_step(W, C);
+  any_node = nl_node > 0;
+  double extra = 0;
+  if (DOUBLE && !SPEC) {  // a second node step in the same iteration (lanes that missed pop in between)
+    const int mp = pop_step(W, C);
+    if (mp) extra += C_POP0 + C_POPIT * mp + 4, C.w_pop++, C.w_popit += mp;
+    const int n2 = node_step(W, C);
+    if (n2) extra += C_NODE + 3, C.w_node++, C.lanes_node += n2;
   }
   if (SPEC) {
     // park leaves: a lane whose cur is a leaf and whose slot is free parks it and pops on
@@ -253,7 +296,7 @@ static void warp_iter(Lane *W, Counts &C) {
     max_pop = std::max(max_pop, it);
   }
   C.w_iters++;
-  double c = C_LOOP;
+  double c = C_LOOP + extra;
   if (any_node) c += C_NODE, C.w_node++, C.lanes_node += nl_node;
   if (any_leaf) c += C_LEAF0 + C_SPH * max_cnt, C.w_leaf++, C.w_leaf_sph += max_cnt, C.lanes_leaf += nl_leaf;
   if (any_pop) c += C_POP0 + C_POPIT * max_pop, C.w_pop++, C.w_popit += max_pop;
@@ -309,6 +352,9 @@ int main(int argc, char **argv) {
     if (!strncmp(argv[i], "keep=", 5)) KEEP = atoi(argv[i] + 5);
     if (!strncmp(argv[i], "leaft=", 6)) LEAF_T = atoi(argv[i] + 6);
     if (!strncmp(argv[i], "one=", 4)) ONE = atoi(argv[i] + 4);
+    if (!strncmp(argv[i], "double=", 7)) DOUBLE = atoi(argv[i] + 7);
+    if (!strncmp(argv[i], "cloop=", 6)) C_LOOP = atoi(argv[i] + 6);
+    if (!strncmp(argv[i], "cnode=", 6)) C_NODE = atoi(argv[i] + 6);
     if (!strncmp(argv[i], "defer=", 6)) DEFER = atoi(argv[i] + 6);
     if (!strncmp(argv[i], "spec=", 5)) SPEC = atoi(argv[i] + 5);
     if (!strncmp(argv[i], "oct=", 4)) OCT = atoi(argv[i] + 4);
