@@ -299,6 +299,23 @@ def test_edge_sizes_against_oracle(W, H, spp, mb):
     assert np.sqrt(np.mean((img32 - ref) ** 2)) <= 0.02
 
 
+@pytest.mark.parametrize("batch", [1024, 5000, 70001])
+def test_small_batches_cross_pass_and_claim_boundaries(monkeypatch, batch):
+    """Batches that are no multiple of the pixel count or of the segment size: the camera-sample enumeration wraps
+    inside claims, chunks end inside segments, and the last batch is ragged.  Float64 mode must still take exactly
+    the oracle's decisions."""
+    monkeypatch.setenv("PTB_BATCH", str(batch))
+    W, H, spp, mb = 61, 37, 9, 6
+    scene = P.shirley_spheres(W, H)
+    img, ref, st, cn = _render_pair(scene, W, H, spp, mb, flags=capi.PTB_FLAG_F64, threads=1)
+    assert list(st.rays_by_bounce[:mb]) == list(cn.rays_by_bounce[:mb])
+    assert st.paths == W * H * spp
+    d = np.abs(img - ref)
+    assert np.mean(d <= 1e-9) >= 0.9995
+    img32 = P.Integrator(scene, W, H, spp, mb).render()
+    assert np.sqrt(np.mean((img32 - ref) ** 2)) <= 0.02
+
+
 def test_raw_and_unfiltered_outputs_compose():
     W, H, spp, mb = 120, 60, 4, 8
     scene = P.shirley_spheres(W, H)
