@@ -87,9 +87,29 @@ Tables<float> &DeviceState::tables<float>() { return tf; }
 template <>
 Tables<double> &DeviceState::tables<double>() { return td; }
 
+// Scene tables come from the device's stream-ordered memory pool, told to keep what is freed: a re-commit then
+// costs microseconds.  cudaMalloc/cudaFree are device-wide synchronisations with page-table updates, and with
+// tens of GB of wavefront queues in the context the dozen of them a commit needs took 250-290 ms.
+static cudaError_t tbl_alloc(void **p, size_t bytes) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  static bool configured[64] = {};
+  if (dev >= 0 && dev < 64 && !configured[dev]) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t keep = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    configured[dev] = true;
+  }
+  return cudaMallocAsync(p, std::max<size_t>(bytes, 16), 0);
+}
+static void tbl_free(void *p) {
+  if (p) cudaFreeAsync(p, 0);
+}
 template <class R>
 static void free_tables(Tables<R> &t) {
-  cudaFree(t.nodes), cudaFree(t.spheres), cudaFree(t.tris), cudaFree(t.tri_uv), cudaFree(t.texs);
+  tbl_free(t.nodes), tbl_free(t.spheres), tbl_free(t.tris), tbl_free(t.tri_uv), tbl_free(t.texs);
   t = Tables<R>();
 }
 template <class R>
@@ -106,8 +126,9 @@ static void free_work(Work<R> &w) {
 void destroy_device_state(DeviceState *d) {
   if (!d) return;
   if (d->device >= 0) cudaSetDevice(d->device);
-  cudaFree(d->sphere_id), cudaFree(d->tri_id), cudaFree(d->sphere_mat), cudaFree(d->tri_mat);
-  cudaFree(d->mats), cudaFree(d->prim_kind);
+  cudaDeviceSynchronize();  // nothing on any stream may still be reading the tables
+  tbl_free(d->sphere_id), tbl_free(d->tri_id), tbl_free(d->sphere_mat), tbl_free(d->tri_mat);
+  tbl_free(d->mats), tbl_free(d->prim_kind);
   free_tables(d->tf), free_tables(d->td);
   delete d;
 }
@@ -127,7 +148,7 @@ template <class T>
 static int upload(T **dst, const std::vector<T> &src) {
   *dst = nullptr;
   size_t bytes = std::max<size_t>(src.size(), 1) * sizeof(T);
-  CK(cudaMalloc((void **)dst, bytes));
+  CK(tbl_alloc((void **)dst, bytes));
   if (!src.empty()) CK(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
   return PTB_OK;
 }
@@ -742,10 +763,10 @@ static int gpu_build_mesh(ptb_scene *s) {
   // outputs
   Tables<float> &t = d->tf;
   free_tables(t);
-  cudaFree(d->sphere_id), cudaFree(d->tri_id), cudaFree(d->sphere_mat), cudaFree(d->tri_mat), cudaFree(d->mats), cudaFree(d->prim_kind);
+  tbl_free(d->sphere_id), tbl_free(d->tri_id), tbl_free(d->sphere_mat), tbl_free(d->tri_mat), tbl_free(d->mats), tbl_free(d->prim_kind);
   d->sphere_id = d->tri_id = d->sphere_mat = d->tri_mat = nullptr, d->mats = nullptr, d->prim_kind = nullptr;
   auto OUT = [&](auto **p, size_t count_) -> int {
-    CK(cudaMalloc((void **)p, std::max<size_t>(count_, 1) * sizeof(**p)));
+    CK(tbl_alloc((void **)p, std::max<size_t>(count_, 1) * sizeof(**p)));
     return PTB_OK;
   };
   G(OUT(&t.nodes, (size_t)n_wide)) G(OUT(&t.spheres, 1)) G(OUT(&t.tris, 3 * (size_t)n)) G(OUT(&t.tri_uv, 6 * (size_t)n))
