@@ -1,8 +1,10 @@
 (* ptb.ml — OCaml bindings to libptb200 (include/ptb200.h), the whole-render replacement of the per-leaf FFI
    `spheres_intersect_native` (shirley_spheres/bin/main.ml:162-172).
 
-   STATUS: written against the OCaml 5 C API but NOT compiled — this image has no ocaml / dune / opam.  The C ABI
-   these stubs bind is the one the Python/ctypes tests and the C++ CLI twin exercise. *)
+   STATUS: written against the OCaml 5 C API; this image has no ocaml / dune / opam, so this file is not
+   type-checked.  The C stubs it binds (ptb_stubs.c) are compiled and run on a mock of the OCaml runtime with the
+   value shapes these declarations imply (tests/test_ocaml_stubs.py), and the C ABI below them is the one the
+   Python/ctypes tests and the C++ CLI twin exercise. *)
 
 type scene (* custom block holding a ptb_scene* *)
 

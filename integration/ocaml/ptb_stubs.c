@@ -1,6 +1,9 @@
 /* ptb_stubs.c — C stubs between OCaml 5 and libptb200 (include/ptb200.h); see ptb.ml.
  *
- * STATUS: NOT compiled here (no OCaml headers in this image).  Same route as sphere-intersect-rs
+ * STATUS: no OCaml toolchain exists in this image, so this file is compiled (-Wall -Werror), linked and RUN against
+ * a mock of the OCaml C runtime (tests/mock_caml/, tests/test_ocaml_stubs.py): every setter's marshalling, the
+ * Failure paths, and — on a GPU box — a render and an intersect_batch whose results equal the ctypes path's.  Not
+ * checked: the real runtime's GC interaction (CAMLparam rooting) and ptb.ml's typing.  Same route as sphere-intersect-rs
  * (sphere-intersect-rs/src/lib.rs:53-76) one level up: one call renders the image.  Unlike that [@@noalloc]
  * per-leaf call, these release the runtime lock around the device work and raise Failure on error
  * (the reference's own style: `failwith`, shape_tree.ml:254-255). */

@@ -2,7 +2,7 @@ import sys, time
 sys.path.insert(0,'/root/repo')
 import numpy as np, torch
 import path_tracer_ocaml_b200 as P
-W,H,SPP,MB=3840,2160,256,8
+W,H,SPP,MB=3840,2160,int(sys.argv[1]) if len(sys.argv)>1 else 256,8
 scene=P.shirley_spheres(W,H)
 integ=P.Integrator(scene,W,H,SPP,MB,device=0)
 host=torch.empty(H,W,3,dtype=torch.float64).pin_memory(); hn=host.numpy()
