@@ -260,10 +260,14 @@ def main():
         e2e_what = ("scene commit (BVH build + table upload) + sharded render + NCCL reduce + resolve + image to "
                     "pinned host memory, wall clock")
     def e2e_step():
+        tc = time.perf_counter()
         scene.commit(local)  # host->device copy of the step's inputs (the scene tables), incl. BVH build
         if world == 1:
+            tr = time.perf_counter()
             integ.render(image=host_np)
             launches[0] += integ.stats.kernel_launches
+            log(f"e2e step: commit {1e3 * (tr - tc):.1f} ms, ptb_render {1e3 * (time.perf_counter() - tr):.1f} ms "
+                f"(device {integ.stats.ms_device:.1f} ms, d2h {integ.stats.ms_d2h:.1f} ms)")
         else:
             step(False)
             if rank == 0:
