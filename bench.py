@@ -354,6 +354,17 @@ def main():
                               "hbm": {"algorithmic_bytes_per_ray": b_ray,
                                       "achieved_gbs": total_rays * b_ray / (total_ms * 1e-3) / 1e9 / world,
                                       "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)"}},
+        # the second kernel: everything of the device time that is not k_trace is k_shade (k_resolve and the batch
+        # bookkeeping are < 0.3 %); it moves 48 B in and 48 B out per scattered hit
+        "roofline_shade": {"bound": "hbm", "kernel": "k_shade<float>",
+                           "achieved": (rays_rank0 - paths_per_step * args.steps / world) * 96.0 /
+                                       (max(timed["ms_device"] - timed["ms_trace"], 1e-9) * 1e-3) / 1e9,
+                           "peak": hbm_peak, "unit": "GB/s",
+                           "frac": (rays_rank0 - paths_per_step * args.steps / world) * 96.0 /
+                                   (max(timed["ms_device"] - timed["ms_trace"], 1e-9) * 1e-3) / 1e9 / hbm_peak,
+                           "algorithmic_bytes_per_hit": 96.0,
+                           "ms_per_step": (timed["ms_device"] - timed["ms_trace"]) / args.steps,
+                           "note": "scattered hits = rays of bounce >= 1 = rays - paths (rank 0)"},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_val, "unit": "Mpaths/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps, "what": e2e_what},
