@@ -454,7 +454,7 @@ static int render_impl(ptb_scene *s, const ptb_params &p, R *d_sums, cudaStream_
   // table look-ups cost nothing and the launch is bound by the memory system alone — which delivers LESS when
   // more warps stream through it at once (measured on the 4K frame: 5.48 / 4.44 / 3.89 / 6.41 ms with 4 / 3 / 2 / 1
   // blocks per SM), while the later, incoherent launches need all the warps they can get to hide their look-ups
-  // (1.6 ms with 4 blocks, 2.0 ms with 2).
+  // (1.6 ms with 4 blocks, 2.0 ms with 2).  Small batches (< 16 Mi paths) do not congest it: they keep 4 too.
   int shade_per_sm0 = std::min(shade_per_sm, 2);
   if (const char *e = std::getenv("PTB_SHADE_BLOCKS0")) shade_per_sm0 = std::min(shade_per_sm, std::max(1, std::atoi(e)));
   const int shade_grid0 = d->sm_count * std::max(shade_per_sm0, 1);
@@ -481,7 +481,7 @@ static int render_impl(ptb_scene *s, const ptb_params &p, R *d_sums, cudaStream_
       if (!last) {
         // a path that is still alive after the last allowed bounce contributes black
         // (integrator.ml:31-32), so the last bounce needs no scatter
-        k_shade<R><<<b == 0 ? shade_grid0 : shade_grid, 256, shade_smem, st>>>(sc, rcst, b, w.mq, (unsigned)w.slots, &ctl->nseg_mat[b][0], w.rays,
+        k_shade<R><<<(b == 0 && n >= (1u << 24)) ? shade_grid0 : shade_grid, 256, shade_smem, st>>>(sc, rcst, b, w.mq, (unsigned)w.slots, &ctl->nseg_mat[b][0], w.rays,
                                                &ctl->nseg_rays[b + 1]);
         ++launches;
       }
