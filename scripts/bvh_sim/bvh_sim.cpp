@@ -57,6 +57,7 @@ static bool sphere_hit(int i, const Ray &r, float &tbest) {
 // ---- policy knobs -------------------------------------------------------------------------------
 static int SORT = 2;   // 0: nearest only, rest in slot order; 1: 3-exchange; 2: full sort
 static int KEEP = 14;  // refill threshold
+static int FULLSORT = 0;  // 1: upper bound — every bounce's rays globally sorted by (direction octant, origin Morton cell)
 static int OCT = 0;    // 1: k_shade bins outgoing rays by direction octant (8 open segments per producer warp)
 static int SPEC = 0;   // 1: speculative traversal: a lane parks ONE leaf and keeps traversing
 static int DEFER = 0;  // 1: flush work runs on full warps of parked results (cost C_FLUSH per 32 rays) + C_PARK per event
@@ -358,6 +359,7 @@ int main(int argc, char **argv) {
     if (!strncmp(argv[i], "defer=", 6)) DEFER = atoi(argv[i] + 6);
     if (!strncmp(argv[i], "spec=", 5)) SPEC = atoi(argv[i] + 5);
     if (!strncmp(argv[i], "oct=", 4)) OCT = atoi(argv[i] + 4);
+    if (!strncmp(argv[i], "fullsort=", 9)) FULLSORT = atoi(argv[i] + 9);
     if (!strncmp(argv[i], "w=", 2)) W = atoi(argv[i] + 2), Hh = W * 9 / 16;
   }
   FILE *f = fopen("/tmp/shirley_scene.bin", "rb");
@@ -453,6 +455,17 @@ int main(int argc, char **argv) {
       }
       for (auto &seg : open) out.insert(out.end(), seg.begin(), seg.end());
       per_bounce[b] = out;
+    }
+    if (FULLSORT && b > 0) {
+      auto key = [](const Ray &r) -> unsigned long long {
+        auto q = [](float v, float lo, float hi) { float t = (v - lo) / (hi - lo); t = t < 0 ? 0 : (t > 0.999f ? 0.999f : t); return (unsigned)(t * 1024); };
+        const unsigned x = q(r.o[0], -15, 15), y = q(r.o[1], -3, 3), z = q(r.o[2], -25, 5);
+        unsigned long long m = 0;
+        for (int b2 = 9; b2 >= 0; --b2) m = (m << 3) | (((x >> b2) & 1) << 2) | (((y >> b2) & 1) << 1) | ((z >> b2) & 1);
+        const unsigned long long o = (r.d[0] < 0) | ((r.d[1] < 0) << 1) | ((r.d[2] < 0) << 2);
+        return FULLSORT == 2 ? ((m >> 12) << 3 | o) : (o << 30 | m);  // 2: coarse cell first, then octant
+      };
+      std::stable_sort(per_bounce[b].begin(), per_bounce[b].end(), [&](const Ray &a, const Ray &c) { return key(a) < key(c); });
     }
     Counts C = simulate(per_bounce[b]);
     printf("%d %8.0f  %6.2f  %6.2f  %6.2f | %8.2f  %6.2f  %5.1f  %5.1f  %5.2f  %5.2f\n", b, C.rays, C.node / C.rays,
