@@ -356,6 +356,9 @@ int main(int argc, char **argv) {
     if (!strncmp(argv[i], "double=", 7)) DOUBLE = atoi(argv[i] + 7);
     if (!strncmp(argv[i], "cloop=", 6)) C_LOOP = atoi(argv[i] + 6);
     if (!strncmp(argv[i], "cnode=", 6)) C_NODE = atoi(argv[i] + 6);
+    if (!strncmp(argv[i], "cflush=", 7)) C_FLUSH = atoi(argv[i] + 7);
+    if (!strncmp(argv[i], "crefill=", 8)) C_REFILL = atoi(argv[i] + 8);
+    if (!strncmp(argv[i], "csph=", 5)) C_SPH = atoi(argv[i] + 5);
     if (!strncmp(argv[i], "defer=", 6)) DEFER = atoi(argv[i] + 6);
     if (!strncmp(argv[i], "spec=", 5)) SPEC = atoi(argv[i] + 5);
     if (!strncmp(argv[i], "oct=", 4)) OCT = atoi(argv[i] + 4);
