@@ -170,9 +170,9 @@ int ptb_scene_get_prim_order(const ptb_scene *s, int32_t *order, int64_t cap) {
 }  // extern "C"
 
 // ---------------------------------------------------------------------------------------------
-// OCaml 5 Stdlib.Random (LXM L64X128, MD5-seeded) as Base.Random.init / Random.float use it
-// (shirley_spheres/bin/main.ml:56,251).  Restated from the OCaml runtime's published algorithm;
-// unverified against a live OCaml (none in this image) — see SURVEY.md App. C.1.
+// OCaml 5 Stdlib.Random (LXM L64X128, MD5-seeded) under Base.Random.init / Base.Random.float
+// (shirley_spheres/bin/main.ml:56,251).  Restated from the OCaml runtime's and Base's published algorithms; no live
+// OCaml in this image, but the resulting sphere field is pinned by the golden image shirley-spheres.png.
 // ---------------------------------------------------------------------------------------------
 namespace {
 
@@ -255,10 +255,18 @@ struct Lxm {
     x0 = q0, x1 = q1;
     return z;
   }
-  double float1() {  // Random.float 1.0
+  // Random.State.bits: 30 bits of one draw (OCaml 5 stdlib random.ml)
+  uint32_t bits30() { return (uint32_t)(next() & 0x3FFFFFFFull); }
+  // Base.Random.float 1.0 — shirley_spheres/bin/main.ml does `open! Base`, so `Random.float` is Base's, not
+  // Stdlib's: two 30-bit draws, ((r1·2^-30) + r2)·2^-30, redrawn when the sum rounds up to 1 (Base random.ml,
+  // third-party; restated from its published source).  Pinned by shirley-spheres.png: the projected small spheres'
+  // albedos agree with the PNG's colours (tests/test_golden_png.py); Stdlib's 53-bit rule does not.
+  double float1() {
     for (;;) {
-      uint64_t n = next() >> 11;
-      if (n != 0) return (double)n * 0x1.0p-53 * 1.0;
+      double r1 = (double)bits30();
+      double r2 = (double)bits30();
+      double x = ((r1 * 0x1.0p-30) + r2) * 0x1.0p-30;
+      if (x < 1.0) return x * 1.0;
     }
   }
 };

@@ -3,10 +3,12 @@
 --max-ray-bounces=8), into a small fixture.  Run in the build container (the PNG does not travel to
 the GPU box):  python tests/golden/make_png_facts.py
 
-Why only these facts: the small-sphere positions/colours come from OCaml's Random, which cannot be
-reproduced here, so only what does not depend on them is pinned — the sky rows
-(camera + background + filter + gamma + 8-bit quantisation), the edge darkening of the 3x3 splat
-(integrator.ml:115-117) and the horizon row."""
+Two fixtures:
+* shirley_png_facts.json — layout-independent facts: the sky rows (camera + background + filter + gamma + 8-bit
+  quantisation), the edge darkening of the 3x3 splat (integrator.ml:115-117) and the horizon row;
+* shirley_png_rgb8.npz — the decoded 300x600x3 uint8 pixels, so that the oracle (and the device) can be compared
+  with the reference's output PIXEL BY PIXEL: with Base.Random.float's two-draw rule the restated scene is the
+  reference's scene and the R2 sampler makes the image deterministic (tests/test_golden_png.py)."""
 import json
 import os
 
@@ -14,7 +16,9 @@ import numpy as np
 from PIL import Image
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-g = np.asarray(Image.open("/root/reference/shirley-spheres.png").convert("RGB")).astype(np.float64)
+g8 = np.asarray(Image.open("/root/reference/shirley-spheres.png").convert("RGB"))
+np.savez_compressed(os.path.join(HERE, "shirley_png_rgb8.npz"), rgb8=g8)
+g = g8.astype(np.float64)
 H, W, _ = g.shape
 # the sky is the smooth region at the top; a row belongs to it while it has no strong horizontal edges
 rows = []
