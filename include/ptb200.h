@@ -22,6 +22,12 @@
  * the tree (shirley_spheres/bin/main.ml:258-260; cornell-box/bin/main.ml:211-218;
  * ganesha/bin/main.ml:74-80).  There is no CPU fallback: every compute entry point fails with
  * PTB_E_NO_DEVICE when no CUDA device is usable.
+ *
+ * Threading: every entry point may be called from any thread (the OCaml stubs release the runtime lock, ctypes
+ * drops the GIL).  The wavefront queues and image buffers belong to the DEVICE, so calls that use the same device —
+ * commit, render, intersect_batch, first_hit, raygen — are serialised by a per-device lock inside the library: two
+ * domains rendering on one GPU take turns, on different GPUs they run concurrently.  A ptb_scene handle itself
+ * must not be modified (set_*, commit, destroy) by one thread while another renders it.
  */
 #ifndef PTB200_H
 #define PTB200_H
@@ -55,8 +61,11 @@ typedef struct ptb_texture {
   double rgb[3];         /* solid only */
 } ptb_texture;
 
-/* Material.t (path_tracer/src/material.ml:3-9): Lambertian tex | Metal tex | Dielectric {index}. */
-enum { PTB_MAT_LAMBERTIAN = 0, PTB_MAT_METAL = 1, PTB_MAT_DIELECTRIC = 2 };
+/* Material.t (path_tracer/src/material.ml:3-9): Lambertian tex | Metal tex | Dielectric {index}.
+ * PTB_MAT_EMISSIVE is an EXTENSION beyond the reference: `Material.emit` is black for every
+ * kind there (material.ml:59); an Emissive tex material returns `Texture.eval tex coord` from that hook and its
+ * `scatter` is `Absorb`, so a path that reaches it ends with `emit0 + attn0 * emit` (integrator.ml:40,43). */
+enum { PTB_MAT_LAMBERTIAN = 0, PTB_MAT_METAL = 1, PTB_MAT_DIELECTRIC = 2, PTB_MAT_EMISSIVE = 3 };
 typedef struct ptb_material {
   int32_t kind;
   int32_t texture; /* Lambertian / Metal: texture row */
@@ -128,6 +137,14 @@ int ptb_scene_set_triangles(ptb_scene *, const double *vx, const double *vy, con
                             int64_t n_vertices, const int32_t *indices, const int32_t *material,
                             const double *uv, int64_t n_triangles);
 int ptb_scene_set_background(ptb_scene *, int32_t kind, const double c0[3], const double c1[3]);
+/* EXTENSION beyond the reference, behind the hook the reference already threads:
+ * `Integrator.create ~diffuse_plus_light` (integrator.mli:13; always `Pdf.diffuse` today, render_command.ml:81;
+ * `Pdf.t` has the single constructor `Diffuse`, pdf.ml:3).  With a light quad set, diffuse scattering samples
+ * `Pdf.Mix (Diffuse, Quad_light {origin; u; v})` — equal weights; the first sample coordinate picks the component —
+ * and weighs the path by `Pdf.eval diffuse / Pdf.eval mix` exactly as integrator.ml:48-66 spells out.  The quad is
+ * the parallelogram origin + a*u + b*v, a, b in [0,1], in camera space; the emitting geometry itself is ordinary
+ * triangles with a PTB_MAT_EMISSIVE material.  NULL origin removes the light (back to `Pdf.diffuse`). */
+int ptb_scene_set_light_quad(ptb_scene *, const double origin[3], const double u[3], const double v[3]);
 /* Shape_tree.create (path_tracer/src/shape_tree.ml:252-263): builds the tree on the host and
  * uploads it to `device`.  Returns build+upload milliseconds through *ms if non-NULL. */
 int ptb_scene_commit(ptb_scene *, int32_t device, double *ms);
@@ -143,6 +160,11 @@ int ptb_scene_tree_stats(const ptb_scene *, int32_t out[8]);
  * image) belong to the DEVICE and are reused between calls: one render or intersect_batch at a time per
  * device and process — like the reference, which renders one image per process. */
 int ptb_render(ptb_scene *, const ptb_params *, double *image_rgb, ptb_stats *);
+/* `update_progress : int -> unit` (integrator.ml:130,150; the Progress bar of render_command.ml:86-104) as a POLLED
+ * counter, because the library never calls back into the host: paths finished / paths in total of the render that
+ * is running (or ran last) on `device`, readable from any other thread while ptb_render / ptb_render_device /
+ * ptb_render_multi is in flight.  The counter advances once per wavefront batch. */
+int ptb_render_progress(int32_t device, uint64_t *paths_done, uint64_t *paths_total);
 
 /* Single-process multi-GPU render (BASELINE.json configs[3]): the scene is replicated on devices
  * 0..n_devices-1 (the tree is built once), device i renders the tiles t = i (mod n_devices) of the reference's tile
@@ -173,6 +195,12 @@ int ptb_intersect_batch(ptb_scene *, const float *origins, const float *directio
 int ptb_intersect_batch_device(ptb_scene *, const float *d_origins, const float *d_directions,
                                float t_min, float t_max, int64_t n, float *d_t_hit, int32_t *d_prim,
                                int32_t device, void *stream, ptb_stats *);
+
+/* Page-locked host memory for callers that want ptb_intersect_batch / ptb_render to copy at full PCIe speed
+ * (the OCaml side would allocate its Bigarrays once through these).  Plain malloc'ed buffers work too; they are
+ * pinned for the duration of a big call (cudaHostRegister) or staged. */
+void *ptb_host_alloc(uint64_t bytes);
+void ptb_host_free(void *);
 
 /* Low_discrepancy_sequence.get (low_discrepancy_sequence.ml:33-36) evaluated ON THE DEVICE by the
  * same device function the ray generator uses: out[i*D + d] for offsets[i], d < D = 2+2*max_bounces.

@@ -15,8 +15,9 @@ extern "C" {
 
 /* shirley_spheres (main.ml:26-110,250-260): ground r=1000 checker, 3 big spheres, 23x23 jittered
  * small spheres drawn from OCaml 5's Random (LXM) seeded with `seed` (the reference uses 42).
- * cam[20] as ptb_camera_create.  The PRNG restatement is unverified against a real OCaml runtime
- * (SURVEY.md App. C.1): the sphere list is input data shared by every implementation. */
+ * cam[20] as ptb_camera_create.  `Random.float` is Base's (main.ml opens Base): two 30-bit draws per float.  With
+ * seed 42 this is the reference's sphere field — the oracle's render of it equals shirley-spheres.png pixel by pixel
+ * (tests/test_golden_png.py). */
 int ptb_scene_load_shirley(ptb_scene *, double aspect, int32_t seed, double cam[20]);
 
 /* cornell-box geometry (main.ml:43-91,170-219): 18 triangles + 3 spheres, camera eye (.5,.5,-1).
@@ -24,6 +25,12 @@ int ptb_scene_load_shirley(ptb_scene *, double aspect, int32_t seed, double cam[
  * c0 / c1 are the caller's choice. */
 int ptb_scene_load_cornell(ptb_scene *, double aspect, int32_t background_kind, const double c0[3],
                            const double c1[3], double cam[20]);
+
+/* EXTENSION (BASELINE.json configs[1] "diffuse+light sampling"; beyond the reference): the
+ * same cornell geometry in a closed, black-background box, lit by an emissive square (PTB_MAT_EMISSIVE, solid
+ * `radiance`) of side 0.1 at the reference's `light_pos` (0.5, 0.82, 0.5) inside the mirror enclosure
+ * (main.ml:184-210), with ptb_scene_set_light_quad on that square. */
+int ptb_scene_load_cornell_lit(ptb_scene *, double aspect, const double radiance[3], double cam[20]);
 
 /* ganesha assembly (ganesha/bin/main.ml:30-119,205-260) from an indexed mesh in WORLD space:
  * camera eye (328,70.282,345)->(328,10,0) fov 30, all faces lambert (0.1,0.7,0.2) with tex
@@ -57,6 +64,7 @@ int ptb_scene_get_triangles(const ptb_scene *, double *vx, double *vy, double *v
                             int32_t *material, double *uv);
 int ptb_scene_get_materials(const ptb_scene *, ptb_material *, ptb_texture *);
 int ptb_scene_get_background(const ptb_scene *, int32_t *kind, double c0[3], double c1[3]);
+int ptb_scene_get_light_quad(const ptb_scene *, int32_t *has_light, double origin[3], double u[3], double v[3]);
 /* reference list order handed to Shape_tree.create: entry >= 0 sphere i, < 0 triangle ~entry */
 int ptb_scene_get_prim_order(const ptb_scene *, int32_t *order, int64_t cap);
 

@@ -10,12 +10,22 @@
 //     Bbox.is_hit (path_tracer_test.ml:121-130), Tile.split/iter (…:34-70), Film_tile coords and
 //     write_pixel locus (…:72-119), unit_square_to_hemisphere norm (…:132-142),
 //     Low_discrepancy_sequence 1-D integrals (low_discrepancy_sequence_test.ml:28-57);
-//   pinned by the reference's one golden artefact shirley-spheres.png, layout-independent facts only
-//     (edge-darkening ratio sqrt(37/48), sky rows, horizon) — tests/golden/shirley_png_facts.json;
-//   PARITY UNPINNED by any reference test or runnable reference (no OCaml/Rust toolchain here, so no
-//     oracle/_ref): Sphere.intersect, the Rust AVX kernel, Triangle.intersect, Shape_tree build and
-//     traversal, Material.scatter, Camera, Integrator.  For those this restatement itself is the
-//     oracle, cross-checked by analytic cases and by scalar-vs-SIMD leaf agreement.
+//   pinned by the reference's one golden artefact shirley-spheres.png (README.md:3,7), PIXEL BY PIXEL: the
+//     600x300 / 32 spp / 8 bounce render of this oracle, quantised floor(255 v), equals the PNG in every byte
+//     of every pixel (tests/test_golden_png.py; fixture tests/golden/shirley_png_rgb8.npz).  That one artefact
+//     exercises and therefore pins: the scene generator (Base.Random.float over OCaml 5's LXM), Camera,
+//     Mat4.look_at, the binned-SAH Shape_tree build and its ordered traversal, Bbox, the Rust AVX sphere kernel
+//     (Simd_leaf), Sphere.hit / tex_coord, Texture (checker), Material.scatter for all three kinds,
+//     Shader_space / Quaternion, the R2 stream, Integrator (dimension consumption, pass*spp offset), Film_tile
+//     splat, stitch, gamma and the PNG quantisation;
+//   PARITY UNPINNED by any reference test, artefact or runnable reference (no OCaml/Rust toolchain here, so no
+//     oracle/_ref): Triangle.intersect / Triangle.Hit.to_hit and the scalar Sphere.intersect inside a mixed
+//     tree (cornell / ganesha geometry — the reference renders those scenes with photon mapping, never through
+//     Integrator).  For those this restatement itself is the oracle, cross-checked by analytic cases and, for the
+//     scalar sphere test, by the `--no-simd` render matching the PNG to +-1 LSB on 99.5 % of the pixels;
+//   EXTENSION, not in the reference (marked EXT below): an emissive material and an area-light
+//     mixture pdf behind the hooks the reference already threads (Material.emit, Hit.emit, Pdf.t,
+//     ~diffuse_plus_light).  Its only oracle is this file.
 //   Third-party behaviour assumed: Base `Float.min/max` propagate NaN; Base `List.min_elt` keeps the
 //     first minimum; `Num.float_of_num` yields the nearest double; glibc libm = OCaml's Float.*.
 #include "oracle.h"
@@ -272,6 +282,9 @@ struct Scene {
   std::vector<Tri> tris;
   int bg_kind = PTB_BG_GRADIENT_Y;
   V3 bg0{1, 1, 1}, bg1{0.5, 0.7, 1.0};
+  // EXT: ~diffuse_plus_light = Pdf.Mix (Diffuse, Quad_light {origin; u; v}) when set, Pdf.diffuse otherwise
+  bool has_light = false;
+  V3 light_o{0, 0, 0}, light_u{1, 0, 0}, light_v{0, 0, 1};
   // tree
   int leaf_kind = ORC_LEAF_SIMD;
   int length_cutoff = 16;
@@ -328,6 +341,8 @@ static Scatter material_scatter(const Scene &s, int m, const ShaderSpace &ss, Te
       out.attenuation = a + c;
       out.ray = ss_world_ray(ss, omega_r);
     }
+  } else if (M.kind == PTB_MAT_EMISSIVE) {
+    out.kind = ABSORB;  // EXT: a light only emits (Material.emit below)
   } else {
     double index = M.index, index_inv = 1.0 / M.index;  // material.ml:13
     double wi_z = omega_i.z;
@@ -346,8 +361,45 @@ static Scatter material_scatter(const Scene &s, int m, const ShaderSpace &ss, Te
   return out;
 }
 
+// Material.emit (material.ml:59): black for every kind of the reference.  EXT: Emissive tex -> Texture.eval tex.
+static V3 material_emit(const Scene &s, int m, TexCoord tc) {
+  const ptb_material &M = s.mat[m];
+  if (M.kind == PTB_MAT_EMISSIVE) return texture_eval(s, M.texture, tc);
+  return {0, 0, 0};
+}
+
 // Pdf.eval Diffuse (pdf.ml:11-15)
 static inline double pdf_eval_diffuse(V3 dir) { return (dir.z < 0.0) ? 0.0 : dir.z / M_PI; }
+
+// EXT — Pdf.Quad_light {origin; u; v}: directions towards a parallelogram light, density with respect to solid
+// angle.  `sample` and `eval` have the signatures of pdf.ml:5-15 (shader space in, shader-space direction out / in).
+static V3 pdf_sample_quad_light(const Scene &sc, const ShaderSpace &ss, double u, double v) {
+  V3 q = (sc.light_o + scale(sc.light_u, u)) + scale(sc.light_v, v);
+  return ss_rotate(ss, normalize(q - ss.origin));
+}
+static double pdf_eval_quad_light(const Scene &sc, V3 dir, const ShaderSpace &ss) {
+  V3 w = ss_rotate_inv(ss, dir);
+  V3 N = cross(sc.light_u, sc.light_v);
+  double nn = dot(N, N);
+  double area = std::sqrt(nn);
+  double denom = dot(w, N) / area;  // cosine at the light
+  if (!(std::fabs(denom) > 1e-9)) return 0.0;
+  double t = (dot(sc.light_o - ss.origin, N) / area) / denom;
+  if (!(t > 1e-9)) return 0.0;
+  V3 rel = (ss.origin + scale(w, t)) - sc.light_o;
+  double a = dot(N, cross(rel, sc.light_v)) / nn, b = dot(N, cross(sc.light_u, rel)) / nn;
+  if (!(0.0 <= a && a <= 1.0 && 0.0 <= b && b <= 1.0)) return 0.0;
+  return (t * t) / (std::fabs(denom) * area);
+}
+// EXT — Pdf.Mix (Diffuse, Quad_light), equal weights; the first coordinate of the 2-D sample picks the component
+// and is stretched back to [0,1)
+static V3 pdf_sample_mix(const Scene &sc, const ShaderSpace &ss, double u, double v) {
+  if (u < 0.5) return unit_square_to_hemisphere(2.0 * u, v);
+  return pdf_sample_quad_light(sc, ss, (2.0 * u) - 1.0, v);
+}
+static double pdf_eval_mix(const Scene &sc, V3 dir, const ShaderSpace &ss) {
+  return 0.5 * (pdf_eval_diffuse(dir) + pdf_eval_quad_light(sc, dir, ss));
+}
 
 // ---------------------------------------------------------------------------------------------
 // sphere.ml (sphere/src/sphere.ml:1-69)
@@ -534,7 +586,7 @@ static inline TexCoord sphere_tex_coord(V3 n) {  // sphere.ml:22-33
   double phi = M_PI + std::atan2(-n.z, n.x);
   return {phi * one_over_two_pi, theta * one_over_pi};
 }
-static Hit sphere_hit(const Sphere &s, double t_hit, const Ray &ray) {  // sphere.ml:56-69
+static Hit sphere_hit(const Scene &sc, const Sphere &s, double t_hit, const Ray &ray) {  // sphere.ml:56-69
   V3 point = point_at(ray, t_hit);
   V3 normal = normalize(point - s.c);  // sphere.ml:21
   bool hit_front = dot(ray.d, normal) < 0.0;
@@ -543,7 +595,7 @@ static Hit sphere_hit(const Sphere &s, double t_hit, const Ray &ray) {  // spher
   h.tc = sphere_tex_coord(normal);
   h.ss = ss_create(normal, point);
   h.mat = s.mat;
-  h.emit = {0, 0, 0};  // Material.emit (material.ml:59)
+  h.emit = material_emit(sc, s.mat, h.tc);  // sphere.ml:65 Material.emit (material.ml:59: black; EXT: Emissive)
   h.omega_i = ss_omega_i(h.ss, ray);
   h.hit_front = hit_front;
   return h;
@@ -564,7 +616,7 @@ static Hit tri_hit(const Scene &sc, const Tri &t, double u, double v, const Ray 
   h.omega_i = ss_omega_i(h.ss, r);
   h.mat = t.mat;
   h.tc = tc;
-  h.emit = {0, 0, 0};  // triangle.ml:63
+  h.emit = material_emit(sc, t.mat, tc);  // triangle.ml:63 writes Color.black; EXT: routed through Material.emit like sphere.ml:65
   h.hit_front = hit_front;
   return h;
 }
@@ -816,7 +868,7 @@ static inline bool scene_intersect(const Scene &sc, const Ray &ray, Hit *hit, or
   cn->hits++;
   int nS = (int)sc.spheres.size();
   if (e.prim < nS)
-    *hit = sphere_hit(sc.spheres[e.prim], e.t, ray);
+    *hit = sphere_hit(sc, sc.spheres[e.prim], e.t, ray);
   else
     *hit = tri_hit(sc, sc.tris[e.prim - nS], e.u, e.v, ray);
   return true;
@@ -1026,13 +1078,15 @@ struct Integrator {
         attn0 = s.attenuation * attn0;
       } else {
         cn->scatter_lambert++;
-        V3 dir = unit_square_to_hemisphere(u, v);  // Pdf.sample (pdf.ml:5-9)
+        // Pdf.sample diffuse_plus_light ss u v (pdf.ml:5-9); diffuse_plus_light = Pdf.diffuse (render_command.ml:81)
+        // unless the scene carries a light (EXT: Pdf.Mix)
+        V3 dir = sc.has_light ? pdf_sample_mix(sc, h.ss, u, v) : unit_square_to_hemisphere(u, v);
         double diffuse_pd = pdf_eval_diffuse(dir);
         if (diffuse_pd == 0.0) {
           cn->absorbed++;
           return add_mul(emit0, attn0, emit);
         }
-        double divisor = pdf_eval_diffuse(dir);  // diffuse_plus_light = Pdf.diffuse (render_command.ml:81)
+        double divisor = sc.has_light ? pdf_eval_mix(sc, dir, h.ss) : pdf_eval_diffuse(dir);
         double pd = diffuse_pd / divisor;
         if (!std::isfinite(pd)) {
           cn->absorbed++;
@@ -1290,6 +1344,10 @@ void orc_scene_set_triangles(orc_scene *s, const double *vx, const double *vy, c
   }
   s->s.committed = false;
 }
+void orc_scene_set_light_quad(orc_scene *s, const double origin[3], const double u[3], const double v[3]) {
+  s->s.has_light = origin != nullptr;
+  if (origin) s->s.light_o = V(origin), s->s.light_u = V(u), s->s.light_v = V(v);
+}
 void orc_scene_set_background(orc_scene *s, int kind, const double c0[3], const double c1[3]) {
   s->s.bg_kind = kind;
   s->s.bg0 = V(c0);
@@ -1389,6 +1447,39 @@ void orc_intersect_batch(orc_scene *s, const double *o, const double *d, double 
     std::memset(cn, 0, sizeof *cn);
     for (auto &c : cns) add_counters(cn, c);
   }
+}
+// The same rays against ONE Array_leaf holding every primitive in set order (Array_leaf.intersect,
+// shape_tree.ml:299-311: linear scan, shrinking t_max): the closest hit without any tree — an independent check
+// for scenes whose reference tree is too expensive to build in a test (10^7 triangles).  Needs no commit.
+void orc_intersect_batch_linear(orc_scene *s, const double *o, const double *d, double t_min, double t_max,
+                                int64_t n, double *t_hit, int32_t *prim, int n_threads) {
+  Scene &sc = s->s;
+  const int saved_kind = sc.leaf_kind;
+  sc.leaf_kind = ORC_LEAF_ARRAY;
+  Leaf all;
+  const int total = (int)(sc.spheres.size() + sc.tris.size());
+  all.prims.resize(total);
+  std::iota(all.prims.begin(), all.prims.end(), 0);
+  int T = std::max(1, n_threads);
+  auto work = [&](int w) {
+    orc_counters cn;
+    std::memset(&cn, 0, sizeof cn);
+    for (int64_t i = n * w / T; i < n * (w + 1) / T; ++i) {
+      Ray r = ray_create(V(o + 3 * i), V(d + 3 * i));
+      EltHit e;
+      if (leaf_intersect(sc, all, r, t_min, t_max, &e, &cn)) {
+        t_hit[i] = e.t;
+        prim[i] = e.prim;
+      } else {
+        t_hit[i] = NAN;
+        prim[i] = -1;
+      }
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int w = 0; w < T; ++w) pool.emplace_back(work, w);
+  for (auto &t : pool) t.join();
+  sc.leaf_kind = saved_kind;
 }
 void orc_first_hit(orc_scene *s, const ptb_params *p, double *t_hit, int32_t *prim, double *cx_out,
                    double *cy_out) {

@@ -74,6 +74,9 @@ void orc_scene_set_triangles(orc_scene *, const double *vx, const double *vy, co
                              int64_t nv, const int32_t *idx, const int32_t *material,
                              const double *uv, int64_t nt);
 void orc_scene_set_background(orc_scene *, int kind, const double c0[3], const double c1[3]);
+/* EXTENSION (not in the reference): ~diffuse_plus_light = Pdf.Mix (Diffuse, Quad_light {origin; u; v}); NULL origin =
+ * back to Pdf.diffuse.  See ptb_scene_set_light_quad in ptb200.h. */
+void orc_scene_set_light_quad(orc_scene *, const double origin[3], const double u[3], const double v[3]);
 /* prim_order: list order handed to Shape_tree.create; entry >= 0 = sphere i, < 0 = triangle ~entry.
  * NULL = spheres then triangles. */
 int orc_scene_commit(orc_scene *, int leaf_kind, int length_cutoff, const int32_t *prim_order,
@@ -96,6 +99,9 @@ void orc_trace_sample(orc_scene *, const ptb_params *, int gx, int gy, int pass,
  * (spheres first, then triangles), -1 on miss */
 void orc_intersect_batch(orc_scene *, const double *o, const double *d, double t_min, double t_max,
                          int64_t n, double *t_hit, int32_t *prim, orc_counters *, int n_threads);
+/* the same against one Array_leaf holding every primitive (shape_tree.ml:299-311): no tree, no commit needed */
+void orc_intersect_batch_linear(orc_scene *, const double *o, const double *d, double t_min, double t_max,
+                                int64_t n, double *t_hit, int32_t *prim, int n_threads);
 /* camera rays of pass 0 for every pixel */
 void orc_first_hit(orc_scene *, const ptb_params *, double *t_hit, int32_t *prim, double *cx,
                    double *cy);

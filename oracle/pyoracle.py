@@ -80,6 +80,7 @@ def lib():
         L.orc_scene_set_spheres.argtypes = [_vp, _dp, _dp, _dp, _dp, _ip, C.c_int64]
         L.orc_scene_set_triangles.argtypes = [_vp, _dp, _dp, _dp, C.c_int64, _ip, _ip, _dp, C.c_int64]
         L.orc_scene_set_background.argtypes = [_vp, C.c_int, _dp, _dp]
+        L.orc_scene_set_light_quad.argtypes = [_vp, _dp, _dp, _dp]
         L.orc_scene_commit.argtypes = [_vp, C.c_int, C.c_int, _ip, C.c_int64]
         L.orc_scene_tree_depth.argtypes = [_vp]
         L.orc_scene_node_count.restype = C.c_int64
@@ -89,6 +90,7 @@ def lib():
         L.orc_trace_sample.argtypes = [_vp, C.POINTER(Params), C.c_int, C.c_int, C.c_int, _dp, C.POINTER(Counters)]
         L.orc_intersect_batch.argtypes = [_vp, _dp, _dp, C.c_double, C.c_double, C.c_int64, _dp, _ip,
                                           C.POINTER(Counters), C.c_int]
+        L.orc_intersect_batch_linear.argtypes = [_vp, _dp, _dp, C.c_double, C.c_double, C.c_int64, _dp, _ip, C.c_int]
         L.orc_first_hit.argtypes = [_vp, C.POINTER(Params), _dp, _ip, _dp, _dp]
         _lib = L
     return _lib
@@ -109,7 +111,7 @@ def d3(v):
 class OracleScene:
     """A scene handed to the oracle as plain tables (the same tables the product's C ABI takes)."""
 
-    def __init__(self, tables, leaf_kind=None, length_cutoff=None, use_ref_order=True):
+    def __init__(self, tables, leaf_kind=None, length_cutoff=None, use_ref_order=True, commit=True):
         L = lib()
         self.h = L.orc_scene_create()
         t = tables
@@ -129,10 +131,14 @@ class OracleScene:
             L.orc_scene_set_triangles(self.h, dptr(vx), dptr(vy), dptr(vz), t["n_vertices"], iptr(idx), iptr(tm),
                                       dptr(uv), t["n_triangles"])
         L.orc_scene_set_background(self.h, t["bg_kind"], dptr(d3(t["bg0"])), dptr(d3(t["bg1"])))
+        if t.get("has_light"):
+            L.orc_scene_set_light_quad(self.h, dptr(d3(t["light_o"])), dptr(d3(t["light_u"])), dptr(d3(t["light_v"])))
         if leaf_kind is None:  # shirley default = Simd_leaf (main.ml:223-226); anything with triangles = Array_leaf
             leaf_kind = ORC_LEAF_SIMD if t["n_triangles"] == 0 else ORC_LEAF_ARRAY
         if length_cutoff is None:
             length_cutoff = 16 if leaf_kind == ORC_LEAF_SIMD else 4
+        if not commit:  # only intersect_batch_linear may be used
+            return
         order = np.ascontiguousarray(t["prim_order"], dtype=np.int32)
         if use_ref_order and len(order):
             rc = L.orc_scene_commit(self.h, leaf_kind, length_cutoff, iptr(order), len(order))
@@ -189,6 +195,14 @@ class OracleScene:
         lib().orc_intersect_batch(self.h, dptr(o), dptr(d), t_min, t_max, n, dptr(t), iptr(prim), C.byref(cn),
                                   n_threads)
         return t, prim, cn
+
+    def intersect_batch_linear(self, o, d, t_min=0.0, t_max=1.7976931348623157e308, n_threads=1):
+        o, d = d3(o).reshape(-1), d3(d).reshape(-1)
+        n = len(o) // 3
+        t = np.zeros(n)
+        prim = np.zeros(n, dtype=np.int32)
+        lib().orc_intersect_batch_linear(self.h, dptr(o), dptr(d), t_min, t_max, n, dptr(t), iptr(prim), n_threads)
+        return t, prim
 
     def tree_stats(self):
         L = lib()

@@ -6,7 +6,8 @@ binds it with ctypes for the tests and ``bench.py``, and mirrors the reference's
 reference's own.  There is no CPU fallback: importing works anywhere, but every compute call raises
 if the CUDA extension is missing or no GPU is present.
 """
+from . import capi  # noqa: F401
 from .capi import lib, PtbError, Params, Stats, Texture, Material  # noqa: F401
-from .scenes import (Scene, shirley_spheres, cornell_box, synthetic_mesh_scene, synthetic_mesh, mesh_scene,  # noqa: F401
+from .scenes import (Scene, shirley_spheres, cornell_box, cornell_box_lit, synthetic_mesh_scene, synthetic_mesh, mesh_scene,  # noqa: F401
                      read_ply_mesh, write_ply_mesh, ganesha)
 from .integrator import Integrator, Args  # noqa: F401

@@ -3,11 +3,10 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# PTB_LIB: development aid for A/B timing of two builds of the SAME library (never a fallback)
-LIB_PATH = os.environ.get("PTB_LIB") or os.path.join(_HERE, "lib", "libptb200.so")
+LIB_PATH = os.path.join(_HERE, "lib", "libptb200.so")  # the one product library; no override, no fallback
 
 PTB_TEX_SOLID, PTB_TEX_CHECKER = 0, 1
-PTB_MAT_LAMBERTIAN, PTB_MAT_METAL, PTB_MAT_DIELECTRIC = 0, 1, 2
+PTB_MAT_LAMBERTIAN, PTB_MAT_METAL, PTB_MAT_DIELECTRIC, PTB_MAT_EMISSIVE = 0, 1, 2, 3
 PTB_BG_CONSTANT, PTB_BG_GRADIENT_Y = 0, 1
 PTB_FLAG_F64, PTB_FLAG_RAW_SUMS, PTB_FLAG_NO_FILTER, PTB_FLAG_PROFILE = 1, 2, 4, 8
 
@@ -55,10 +54,14 @@ SYMBOLS = {
     "ptb_scene_set_spheres": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _ip, C.c_int64]),
     "ptb_scene_set_triangles": (C.c_int, [_vp, _dp, _dp, _dp, C.c_int64, _ip, _ip, _dp, C.c_int64]),
     "ptb_scene_set_background": (C.c_int, [_vp, C.c_int32, _dp, _dp]),
+    "ptb_scene_set_light_quad": (C.c_int, [_vp, _dp, _dp, _dp]),
     "ptb_scene_commit": (C.c_int, [_vp, C.c_int32, _dp]),
     "ptb_scene_primitive_count": (C.c_int64, [_vp]),
     "ptb_scene_tree_stats": (C.c_int, [_vp, _ip]),
     "ptb_render": (C.c_int, [_vp, _P(Params), _dp, _P(Stats)]),
+    "ptb_render_progress": (C.c_int, [C.c_int32, _P(C.c_uint64), _P(C.c_uint64)]),
+    "ptb_host_alloc": (_vp, [C.c_uint64]),
+    "ptb_host_free": (None, [_vp]),
     "ptb_scene_commit_multi": (C.c_int, [_vp, C.c_int32, _dp]),
     "ptb_render_multi": (C.c_int, [_vp, _P(Params), C.c_int32, _dp, _P(Stats)]),
     "ptb_render_device": (C.c_int, [_vp, _P(Params), _vp, _vp, _P(Stats)]),
@@ -79,6 +82,8 @@ SYMBOLS = {
     # ptb200_scenes.h
     "ptb_scene_load_shirley": (C.c_int, [_vp, C.c_double, C.c_int32, _dp]),
     "ptb_scene_load_cornell": (C.c_int, [_vp, C.c_double, C.c_int32, _dp, _dp, _dp]),
+    "ptb_scene_load_cornell_lit": (C.c_int, [_vp, C.c_double, _dp, _dp]),
+    "ptb_scene_get_light_quad": (C.c_int, [_vp, _ip, _dp, _dp, _dp]),
     "ptb_scene_load_mesh": (C.c_int, [_vp, _fp, C.c_int64, _ip, C.c_int64, C.c_double, _dp]),
     "ptb_mesh_synthetic": (C.c_int, [C.c_int64, C.c_uint32, _fp, C.c_int64, _ip, C.c_int64,
                                      _P(C.c_int64), _P(C.c_int64)]),
@@ -127,3 +132,20 @@ def fptr(a):
 
 def iptr(a):
     return a.ctypes.data_as(_ip)
+
+
+def pinned_empty(shape, dtype):
+    """A numpy array over page-locked host memory from ptb_host_alloc (what a host that wants full PCIe speed
+    hands to ptb_intersect_batch / ptb_render).  The memory is released when the array is garbage-collected."""
+    import numpy as np
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape)) if not isinstance(shape, int) else int(shape)
+    nbytes = max(n * dt.itemsize, 1)
+    p = lib().ptb_host_alloc(nbytes)
+    if not p:
+        raise PtbError(f"ptb_host_alloc({nbytes}) failed: {lib().ptb_last_error().decode()}")
+    buf = (C.c_char * nbytes).from_address(p)
+    arr = np.frombuffer(buf, dtype=dt, count=n).reshape(shape)
+    import weakref
+    weakref.finalize(buf, lib().ptb_host_free, p)
+    return arr

@@ -6,7 +6,9 @@
 // printed lines, plus the device flag the port adds.  One binary, dispatching on its name or first argument:
 //
 //   shirley_spheres --dimension=600,300 --samples-per-pixel=32 --max-ray-bounces=8 [-o out.png] [--no-simd]
-//   cornell_box     -d 1024,1024 --samples-per-pixel=256 --max-ray-bounces=16 [--background white|sky]
+//   cornell_box     -d 1024,1024 --samples-per-pixel=256 --max-ray-bounces=16 [--background white|sky|light]
+//                   (light: closed black box lit by an emissive square, sampled through diffuse_plus_light — the
+//                    extension behind BASELINE.json configs[1])
 //   ganesha         -d 1920,1080 --samples-per-pixel=256 (--ganesha-ply FILE | --synthetic-faces N)
 //   common: [--no-progress] [--device cuda[:N]] [--gpus N] [--f64]   (output *.ppm writes a PPM instead of a PNG)
 //
@@ -18,7 +20,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/ptb200.h"
@@ -163,7 +167,9 @@ int main(int argc, char **argv) {
     check(ptb_scene_load_shirley(sc, aspect, 42, cam), "shirley scene");  // Random.init 42 (main.ml:251)
   } else if (name == "cornell_box") {
     const double white[3] = {1, 1, 1}, sky0[3] = {1, 1, 1}, sky1[3] = {0.5, 0.7, 1.0};
-    if (a.background == "sky") check(ptb_scene_load_cornell(sc, aspect, PTB_BG_GRADIENT_Y, sky0, sky1, cam), "cornell scene");
+    const double radiance[3] = {32, 32, 32};
+    if (a.background == "light") check(ptb_scene_load_cornell_lit(sc, aspect, radiance, cam), "cornell scene");
+    else if (a.background == "sky") check(ptb_scene_load_cornell(sc, aspect, PTB_BG_GRADIENT_Y, sky0, sky1, cam), "cornell scene");
     else check(ptb_scene_load_cornell(sc, aspect, PTB_BG_CONSTANT, white, nullptr, cam), "cornell scene");
   } else if (name == "ganesha") {
     float *xyz = nullptr;
@@ -206,10 +212,31 @@ int main(int argc, char **argv) {
   p.tile_rank = 0, p.tile_world = 1, p.flags = a.f64 ? PTB_FLAG_F64 : 0, p.device = a.device;
   std::vector<double> image((size_t)3 * a.width * a.height);
   ptb_stats st;
+  // Progress bar (render_command.ml:86-104: `Progress.with_reporter` fed by update_progress with tile areas): a thread
+  // polls the library's path counter while the render call blocks this one; --no-progress switches it off
+  std::atomic<bool> rendering{true};
+  std::thread bar;
+  if (!a.no_progress)
+    bar = std::thread([&] {
+      uint64_t done = 0, total = 0, shown = ~0ull;
+      while (rendering.load()) {
+        if (ptb_render_progress(a.device, &done, &total) == 0 && total && done != shown) {
+          const int w = 40, fill = (int)((double)done / (double)total * w);
+          std::fprintf(stderr, "\rRendering [%.*s%*s] %3d%%", fill, "########################################", w - fill, "",
+                       (int)(100.0 * (double)done / (double)total));
+          std::fflush(stderr);
+          shown = done;
+        }
+        std::this_thread::sleep_for(std::chrono::milliseconds(50));
+      }
+      if (shown != ~0ull) std::fprintf(stderr, "\rRendering [########################################] 100%%\n");
+    });
   auto t0 = clk::now();
-  if (a.gpus > 1) check(ptb_render_multi(sc, &p, a.gpus, image.data(), &st), "render");
-  else check(ptb_render(sc, &p, image.data(), &st), "render");
+  int rrc = a.gpus > 1 ? ptb_render_multi(sc, &p, a.gpus, image.data(), &st) : ptb_render(sc, &p, image.data(), &st);
   const double ms = std::chrono::duration<double, std::milli>(clk::now() - t0).count();
+  rendering.store(false);
+  if (bar.joinable()) bar.join();
+  check(rrc, "render");
   // Bimage_unix.Stb.write of an f64 image: 8-bit, truncating (pinned by the sky rows of the golden PNG,
   // tests/golden/shirley_png_facts.json), clamped to [0, 255]
   std::vector<unsigned char> rgb(image.size());

@@ -67,6 +67,9 @@ struct DScene {
   int32_t stack_cap;      // traversal stack entries per thread
   int32_t bg_kind;
   R bg0[3], bg1[3];
+  // extension (ptb_scene_set_light_quad / PTB_MAT_EMISSIVE): diffuse_plus_light = Mix (Diffuse, Quad_light)
+  int32_t has_light, has_emissive;
+  R light_o[3], light_u[3], light_v[3];
 };
 
 // Wavefront queue entry = three Vec4 (48 B in float):

@@ -1079,7 +1079,7 @@ __host__ __device__ constexpr size_t shade_smem_bytes(unsigned block) {
 template <class R>
 __global__ void __launch_bounds__(256)
     k_shade(DScene<R> sc, RenderConst rc, int bounce, Queue<R> q0, unsigned q_slots,
-            unsigned *__restrict__ nseg_mat, Queue<R> out, unsigned *__restrict__ nseg_out) {
+            unsigned *__restrict__ nseg_mat, Queue<R> out, unsigned *__restrict__ nseg_out, R *__restrict__ sums, int last) {
   // Software pipeline over the warp's work items (one item = 32 entries of one segment of one material's hit
   // queue): while item k is shaded, the 48 B entries of items k+1 .. k+SHADE_NBUF-1 and the fill counts of their
   // segments are in flight into shared memory (cp.async: no register and no scoreboard is tied up, each lane
@@ -1253,15 +1253,65 @@ __global__ void __launch_bounds__(256)
       }
       const V3<R> attn0 = {C.x, C.y, C.z};
       V3<R> dir_ss = {R(0), R(0), R(1)};
-      if (m == PTB_MAT_LAMBERTIAN) {
-        // Scatter.Diffuse; Pdf.sample = cosine hemisphere (pdf.ml:5-9, shader_space.ml:56-64);
-        // diffuse_pd / divisor == 1 exactly, diffuse_pd = 0 iff z = 0 (integrator.ml:48-58)
-        R u = r_min(R(ud), Lim<R>::below_one()), sn, cs;
-        R rr = r_sqrt_fast(u);  // float: MUFU.SQRT (2 ulp); double: exact
-        r_sincos2pi(R(vd), &sn, &cs);
-        dir_ss = {rr * cs, rr * sn, r_sqrt_fast(R(1) - u)};
-        alive = dir_ss.z > R(0);
-        nattn = {albedo.x * attn0.x, albedo.y * attn0.y, albedo.z * attn0.z};
+      if (m == PTB_MAT_LAMBERTIAN && mat.kind == PTB_MAT_EMISSIVE) {
+        // extension: Material.emit = the texture, scatter = Absorb -> the path ends with emit0 + attn0 * emit
+        // (integrator.ml:40,43; emit0 == 0 on every path because the only emitting kind absorbs).  Emissive hits
+        // travel in the Lambertian queue.
+        const int pixel = r2i(A.w);
+        atomicAdd(&sums[3 * (size_t)pixel + 0], attn0.x * albedo.x);
+        atomicAdd(&sums[3 * (size_t)pixel + 1], attn0.y * albedo.y);
+        atomicAdd(&sums[3 * (size_t)pixel + 2], attn0.z * albedo.z);
+      } else if (last) {
+        // the path has used its max_bounces intersections: whatever it would scatter contributes black
+        // (integrator.ml:31-32); this launch exists only to collect the emission above
+      } else if (m == PTB_MAT_LAMBERTIAN) {
+        // Scatter.Diffuse; Pdf.sample diffuse_plus_light (pdf.ml:5-9, shader_space.ml:56-64)
+        if (!sc.has_light) {
+          // diffuse_plus_light = Pdf.diffuse (render_command.ml:81): diffuse_pd / divisor == 1 exactly,
+          // diffuse_pd = 0 iff z = 0 (integrator.ml:48-58)
+          R u = r_min(R(ud), Lim<R>::below_one()), sn, cs;
+          R rr = r_sqrt_fast(u);  // float: MUFU.SQRT (2 ulp); double: exact
+          r_sincos2pi(R(vd), &sn, &cs);
+          dir_ss = {rr * cs, rr * sn, r_sqrt_fast(R(1) - u)};
+          alive = dir_ss.z > R(0);
+          nattn = {albedo.x * attn0.x, albedo.y * attn0.y, albedo.z * attn0.z};
+        } else {
+          // extension: Pdf.Mix (Diffuse, Quad_light) — the first coordinate picks the component (ptb200.h)
+          const V3<R> lo = {sc.light_o[0], sc.light_o[1], sc.light_o[2]}, lu = {sc.light_u[0], sc.light_u[1], sc.light_u[2]},
+                      lv = {sc.light_v[0], sc.light_v[1], sc.light_v[2]};
+          if (ud < 0.5) {
+            R u = r_min(R(2.0 * ud), Lim<R>::below_one()), sn, cs;
+            R rr = r_sqrt_fast(u);
+            r_sincos2pi(R(vd), &sn, &cs);
+            dir_ss = {rr * cs, rr * sn, r_sqrt_fast(R(1) - u)};
+          } else {
+            const R lu_ = R((2.0 * ud) - 1.0), lv_ = R(vd);
+            const V3<R> q = (lo + lu * lu_) + lv * lv_;
+            dir_ss = quat_transform(frame, normalize(q - p));
+          }
+          const R PI = R(3.141592653589793);
+          const R diffuse_pd = dir_ss.z < R(0) ? R(0) : dir_ss.z / PI;  // Pdf.eval Pdf.diffuse (pdf.ml:11-15)
+          // Pdf.eval Quad_light: solid-angle density of the direction on the parallelogram
+          R light_pd = R(0);
+          {
+            const V3<R> w = quat_transform(frame_inv, dir_ss);
+            const V3<R> N = cross(lu, lv);
+            const R nn = dot(N, N), area = r_sqrt(nn), denom = dot(w, N) / area;
+            if (r_abs(denom) > R(1e-9)) {
+              const R t = (dot(lo - p, N) / area) / denom;
+              if (t > R(1e-9)) {
+                const V3<R> rel = (p + w * t) - lo;
+                const R a = dot(N, cross(rel, lv)) / nn, b = dot(N, cross(lu, rel)) / nn;
+                if (R(0) <= a && a <= R(1) && R(0) <= b && b <= R(1)) light_pd = (t * t) / (r_abs(denom) * area);
+              }
+            }
+          }
+          const R divisor = R(0.5) * (diffuse_pd + light_pd);
+          const R pd = diffuse_pd / divisor;  // integrator.ml:55
+          alive = diffuse_pd != R(0) && isfinite(pd);  // integrator.ml:51,56
+          const V3<R> att = {pd * albedo.x, pd * albedo.y, pd * albedo.z};  // Color.scale attenuation pd (integrator.ml:60)
+          nattn = {att.x * attn0.x, att.y * attn0.y, att.z * attn0.z};
+        }
       } else if (m == PTB_MAT_METAL) {
         // material.ml:28-44: mirror, Schlick-tinted; omega_r.z <= 0 -> Absorb
         dir_ss = {-wi.x, -wi.y, wi.z};
@@ -1305,8 +1355,13 @@ __global__ void __launch_bounds__(256)
 
 // batch bookkeeping: fold the finished batch's ray counts into the totals, reset the counters and
 // publish the next batch's ray-queue segment count.
-__global__ void k_batch_ctl(Ctl *ctl, unsigned next_n, int max_bounces) {
+__global__ void k_batch_ctl(Ctl *ctl, unsigned next_n, int max_bounces, unsigned long long *progress,
+                            unsigned long long paths_done) {
   const int t = threadIdx.x;
+  if (t == 0 && progress) {  // polled by ptb_render_progress: zero-copy host memory
+    *reinterpret_cast<volatile unsigned long long *>(progress) = paths_done;
+    __threadfence_system();
+  }
   if (t < max_bounces) {  // only bounces that were actually traced (integrator.ml:31-32)
     unsigned v = ctl->n_rays[t];
     ctl->rays_by_bounce[t] += v;
@@ -1359,7 +1414,8 @@ struct PeerPtrs {
   int n;
 };
 __global__ void __launch_bounds__(256) k_reduce_peers(float *__restrict__ dst, PeerPtrs pp, size_t n) {
-  const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;  // grid covers ceil(n / 4) threads
+  if (i >= n) return;
   if (i + 3 < n) {
     float4 a = *reinterpret_cast<const float4 *>(dst + i);
     for (int k = 0; k < pp.n; ++k) {

@@ -14,6 +14,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -147,12 +149,15 @@ int parse(const unsigned char *b, long long len, std::vector<float> *xyz, std::v
         return fail(PTB_E_INVALID, "expected integer type in list property " + p.name);  // int_accessor_exn
       const bool want = p.name == "vertex_indices";
       const int ls = size_of(p.len_type), es = size_of(p.type);
+      // the header is untrusted: a list row takes at least its length field, so a count the rest of the file
+      // cannot hold is rejected before anything is sized from it
+      if (e.count > (len - pos) / std::max(ls, 1)) return fail(PTB_E_INVALID, "ply body is truncated (element " + e.name + ")");
       if (want) faces->reserve((size_t)e.count * 3);
       for (long long i = 0; i < e.count; ++i) {
         if (pos + ls > len) return fail(PTB_E_INVALID, "ply body is truncated (element " + e.name + ")");
         long long n = read_int(b + pos, p.len_type);
         pos += ls;
-        if (n < 0 || pos + n * es > len) return fail(PTB_E_INVALID, "ply body is truncated (element " + e.name + ")");
+        if (n < 0 || n > (len - pos) / std::max(es, 1)) return fail(PTB_E_INVALID, "ply body is truncated (element " + e.name + ")");
         if (want) {
           if (n != 3) return fail(PTB_E_INVALID, "expected every face to have exactly 3 vertices");  // ganesha main.ml:182-185
           for (int k = 0; k < 3; ++k) faces->push_back((int32_t)read_int(b + pos + k * es, p.type));
@@ -169,7 +174,8 @@ int parse(const unsigned char *b, long long len, std::vector<float> *xyz, std::v
           if (p.name == (a == 0 ? "x" : a == 1 ? "y" : "z")) off[a] = (int)width, ty[a] = p.type;
         width += size_of(p.type);
       }
-      if (pos + width * e.count > len) return fail(PTB_E_INVALID, "ply body is truncated (element " + e.name + ")");
+      if (e.count > (len - pos) / std::max<long long>(width, 1))  // (division: width * count must not overflow)
+        return fail(PTB_E_INVALID, "ply body is truncated (element " + e.name + ")");
       if (e.name == "vertex") {
         for (int a = 0; a < 3; ++a) {
           if (off[a] < 0) return fail(PTB_E_INVALID, "vertex element has no x/y/z property");
@@ -216,11 +222,17 @@ extern "C" {
 
 int ptb_ply_parse_mesh(const void *bytes, int64_t len, float **xyz, int64_t *n_vertices, int32_t **faces, int64_t *n_faces) {
   if (!bytes || !xyz || !n_vertices || !faces || !n_faces || len < 0) return fail(PTB_E_INVALID, "ply_parse_mesh: bad args");
-  std::vector<float> v;
-  std::vector<int32_t> f;
-  int rc = parse((const unsigned char *)bytes, len, &v, &f);
-  if (rc) return rc;
-  return hand_over(v, f, xyz, n_vertices, faces, n_faces);
+  try {  // nothing may unwind through the C ABI into OCaml / Python / the CLI
+    std::vector<float> v;
+    std::vector<int32_t> f;
+    int rc = parse((const unsigned char *)bytes, len, &v, &f);
+    if (rc) return rc;
+    return hand_over(v, f, xyz, n_vertices, faces, n_faces);
+  } catch (const std::bad_alloc &) {
+    return fail(PTB_E_NOMEM, "ply: out of memory");
+  } catch (const std::exception &e) {
+    return fail(PTB_E_INVALID, std::string("ply: ") + e.what());
+  }
 }
 
 int ptb_ply_read_mesh(const char *path, float **xyz, int64_t *n_vertices, int32_t **faces, int64_t *n_faces) {
@@ -230,7 +242,13 @@ int ptb_ply_read_mesh(const char *path, float **xyz, int64_t *n_vertices, int32_
   std::fseek(f, 0, SEEK_END);
   long long n = std::ftell(f);
   std::fseek(f, 0, SEEK_SET);
-  std::vector<unsigned char> buf((size_t)std::max<long long>(n, 0));
+  std::vector<unsigned char> buf;
+  try {
+    buf.resize((size_t)std::max<long long>(n, 0));
+  } catch (const std::exception &) {
+    std::fclose(f);
+    return fail(PTB_E_NOMEM, "ply: out of memory");
+  }
   size_t got = buf.empty() ? 0 : std::fread(buf.data(), 1, buf.size(), f);
   std::fclose(f);
   if ((long long)got != n) return fail(PTB_E_INVALID, std::string("short read on ") + path);

@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -30,6 +31,7 @@ struct Tables {
   R *tri_uv = nullptr;
   DTex<R> *texs = nullptr;
   bool ready = false;
+  bool in_blob = false;  // the pointers are slices of DeviceState::blob (freed with it)
 };
 // producer warps that may each leave one partially filled segment behind in a queue (upper bound over
 // every launch shape used here), i.e. the slack a segmented queue needs on top of its dense capacity
@@ -45,9 +47,22 @@ struct Work {
 // Per-device work buffers (wavefront queues, control block, pixel list).  They belong to the device,
 // not to a scene: committing another scene must not reallocate gigabytes of queue memory.
 struct DevicePool {
+  // Serialises every entry point that uses this device's work buffers (ptb200.h "Threading"): the OCaml stubs release
+  // the runtime lock and ctypes drops the GIL, so two host threads can be inside the library at once.  Recursive:
+  // ptb_intersect_batch calls ptb_intersect_batch_device, a commit of a replica happens inside commit_multi.
+  std::recursive_mutex mu;
   Work<float> wf;
   Work<double> wd;
   Ctl *ctl = nullptr;
+  // polled progress (ptb_render_progress): a zero-copy host word the batch-control kernel stores into
+  unsigned long long *progress_host = nullptr, *progress_dev = nullptr;
+  unsigned long long progress_total = 0;
+  // cached device properties (cudaGetDeviceProperties costs milliseconds; a re-commit must not pay it again)
+  int sm_count = 0;
+  size_t smem_optin = 0;
+  // pinned staging: one block for the scene tables of a commit, two chunk buffers for ptb_intersect_batch
+  void *stage_host = nullptr;
+  size_t stage_cap = 0;
   // ptb_render's device image buffers (per-pixel sums and the resolved image), grown on demand and kept:
   // allocating and freeing ~300 MB per call costs tens to hundreds of ms of host time on a busy allocator
   void *sums_buf = nullptr, *img_buf = nullptr;
@@ -68,6 +83,7 @@ static DevicePool *pool_for(int device) {
   static DevicePool pools[64];
   return &pools[device & 63];
 }
+using PoolLock = std::lock_guard<std::recursive_mutex>;
 
 struct DeviceState {
   int device = -1;
@@ -76,6 +92,9 @@ struct DeviceState {
   int32_t *sphere_id = nullptr, *tri_id = nullptr, *sphere_mat = nullptr, *tri_mat = nullptr;
   DMat *mats = nullptr;
   uint8_t *prim_kind = nullptr;
+  // host-built trees: every float-path table above and in `tf` is a slice of ONE allocation filled by ONE copy
+  void *blob = nullptr;
+  bool ids_in_blob = false;
   Tables<float> tf;
   Tables<double> td;
   DevicePool *pool = nullptr;
@@ -109,7 +128,7 @@ static void tbl_free(void *p) {
 }
 template <class R>
 static void free_tables(Tables<R> &t) {
-  tbl_free(t.nodes), tbl_free(t.spheres), tbl_free(t.tris), tbl_free(t.tri_uv), tbl_free(t.texs);
+  if (!t.in_blob) tbl_free(t.nodes), tbl_free(t.spheres), tbl_free(t.tris), tbl_free(t.tri_uv), tbl_free(t.texs);
   t = Tables<R>();
 }
 template <class R>
@@ -123,13 +142,23 @@ static void free_work(Work<R> &w) {
   free_queue(w.mq);
   w.cap = 0, w.slots = 0;
 }
+// releases every table of `d` (stream-ordered frees: cheap, the pool keeps the memory) but keeps the state object
+static void release_device_tables(DeviceState *d) {
+  if (!d->ids_in_blob) {
+    tbl_free(d->sphere_id), tbl_free(d->tri_id), tbl_free(d->sphere_mat), tbl_free(d->tri_mat);
+    tbl_free(d->mats), tbl_free(d->prim_kind);
+  }
+  d->sphere_id = d->tri_id = d->sphere_mat = d->tri_mat = nullptr, d->mats = nullptr, d->prim_kind = nullptr;
+  free_tables(d->tf), free_tables(d->td);
+  tbl_free(d->blob);
+  d->blob = nullptr, d->ids_in_blob = false;
+}
 void destroy_device_state(DeviceState *d) {
   if (!d) return;
   if (d->device >= 0) cudaSetDevice(d->device);
+  PoolLock lk(pool_for(d->device)->mu);
   cudaDeviceSynchronize();  // nothing on any stream may still be reading the tables
-  tbl_free(d->sphere_id), tbl_free(d->tri_id), tbl_free(d->sphere_mat), tbl_free(d->tri_mat);
-  tbl_free(d->mats), tbl_free(d->prim_kind);
-  free_tables(d->tf), free_tables(d->td);
+  release_device_tables(d);
   delete d;
 }
 
@@ -176,15 +205,18 @@ float box_hi<float>(double x, double ext) {
 }
 
 template <class R>
-static int ensure_tables(ptb_scene *s) {
-  DeviceState *d = s->dev;
-  Tables<R> &t = d->tables<R>();
-  if (t.ready) return PTB_OK;
+struct HostTables {
+  std::vector<Node4<R>> nodes;
+  std::vector<Vec4<R>> sph, tri;
+  std::vector<R> uv;
+  std::vector<DTex<R>> texs;
+};
+template <class R>
+static void make_host_tables(const ptb_scene *s, HostTables<R> *out) {
   const HostScene &h = s->host;
   const WideBVH &b = s->bvh;
-  if (b.device_built)
-    return fail(PTB_E_UNSUPPORTED, "this scene's tree was built on the device (float32 tables only): use PTB_BUILDER=host for PTB_FLAG_F64");
-  std::vector<Node4<R>> nodes(b.nodes.size());
+  std::vector<Node4<R>> &nodes = out->nodes;
+  nodes.resize(b.nodes.size());
   for (size_t i = 0; i < nodes.size(); ++i) {
     for (int k = 0; k < 4; ++k) {
       double ext = 0;
@@ -196,13 +228,16 @@ static int ensure_tables(ptb_scene *s) {
       nodes[i].child[k] = b.nodes[i].child[k];
     }
   }
-  std::vector<Vec4<R>> sph(b.sphere_order.size());
+  std::vector<Vec4<R>> &sph = out->sph;
+  sph.resize(b.sphere_order.size());
   for (size_t k = 0; k < sph.size(); ++k) {
     int i = b.sphere_order[k];
     sph[k] = {(R)h.sx[i], (R)h.sy[i], (R)h.sz[i], (R)h.sr[i]};
   }
-  std::vector<Vec4<R>> tri(3 * b.tri_order.size());
-  std::vector<R> uv(6 * b.tri_order.size());
+  std::vector<Vec4<R>> &tri = out->tri;
+  std::vector<R> &uv = out->uv;
+  tri.resize(3 * b.tri_order.size());
+  uv.resize(6 * b.tri_order.size());
   for (size_t k = 0; k < b.tri_order.size(); ++k) {
     int i = b.tri_order[k];
     int ia = h.tidx[3 * i], ib = h.tidx[3 * i + 1], ic = h.tidx[3 * i + 2];
@@ -211,17 +246,31 @@ static int ensure_tables(ptb_scene *s) {
     tri[3 * k + 2] = {(R)(h.vx[ic] - h.vx[ia]), (R)(h.vy[ic] - h.vy[ia]), (R)(h.vz[ic] - h.vz[ia]), R(0)};
     for (int c = 0; c < 6; ++c) uv[6 * k + c] = (R)h.tuv[6 * i + c];
   }
-  std::vector<DTex<R>> texs(h.tex.size());
+  std::vector<DTex<R>> &texs = out->texs;
+  texs.resize(h.tex.size());
   for (size_t i = 0; i < texs.size(); ++i) {
     const ptb_texture &x = h.tex[i];
     texs[i] = {x.kind, x.width, x.height, x.even, x.odd, 0, {(R)x.rgb[0], (R)x.rgb[1], (R)x.rgb[2]}};
   }
+}
+
+// The float tables are uploaded by the commit (upload_scene: one blob, one copy).  The float64 tables of the
+// validation mode are made on first use, table by table.
+template <class R>
+static int ensure_tables(ptb_scene *s) {
+  DeviceState *d = s->dev;
+  Tables<R> &t = d->tables<R>();
+  if (t.ready) return PTB_OK;
+  if (s->bvh.device_built)
+    return fail(PTB_E_UNSUPPORTED, "this scene's tree was built on the device (float32 tables only): use PTB_BUILDER=host for PTB_FLAG_F64");
+  HostTables<R> ht;
+  make_host_tables<R>(s, &ht);
   int rc;
-  if ((rc = upload(&t.nodes, nodes))) return rc;
-  if ((rc = upload(&t.spheres, sph))) return rc;
-  if ((rc = upload(&t.tris, tri))) return rc;
-  if ((rc = upload(&t.tri_uv, uv))) return rc;
-  if ((rc = upload(&t.texs, texs))) return rc;
+  if ((rc = upload(&t.nodes, ht.nodes))) return rc;
+  if ((rc = upload(&t.spheres, ht.sph))) return rc;
+  if ((rc = upload(&t.tris, ht.tri))) return rc;
+  if ((rc = upload(&t.tri_uv, ht.uv))) return rc;
+  if ((rc = upload(&t.texs, ht.texs))) return rc;
   t.ready = true;
   return PTB_OK;
 }
@@ -317,6 +366,10 @@ static DScene<R> make_dscene(ptb_scene *s, size_t *scene_bytes_out) {
   sc.scene_in_smem = (bytes <= 100 * 1024 && s->bvh.max_stack + 1 <= sc.stack_cap) ? 1 : 0;
   sc.bg_kind = s->host.bg_kind;
   for (int i = 0; i < 3; ++i) sc.bg0[i] = (R)s->host.bg0[i], sc.bg1[i] = (R)s->host.bg1[i];
+  sc.has_light = s->host.has_light ? 1 : 0;
+  sc.has_emissive = s->host.has_emissive() ? 1 : 0;
+  for (int i = 0; i < 3; ++i)
+    sc.light_o[i] = (R)s->host.light_o[i], sc.light_u[i] = (R)s->host.light_u[i], sc.light_v[i] = (R)s->host.light_v[i];
   *scene_bytes_out = sc.scene_in_smem ? bytes : 0;
   return sc;
 }
@@ -398,7 +451,8 @@ static void launch_trace(const TraceLaunch &tl, cudaStream_t st, const DScene<R>
 // Paths per wavefront batch.  Bigger batches mean fewer, longer launches (less tail and launch overhead per ray:
 // 32 Mi -> 256 Mi paths is -7 % trace time); the queues of a 256 Mi batch take 52 GB of the 180 GB, and the size
 // is halved until they fit in 60 % of the memory that is free.
-static size_t batch_capacity(size_t have /* capacity of the queues the device pool already holds */) {
+static size_t batch_capacity(size_t have /* capacity of the queues the device pool already holds */,
+                             size_t vec4_bytes /* sizeof(Vec4<R>) of the pipeline that will run */) {
   size_t nb = (size_t)1 << 28;
   if (const char *e = std::getenv("PTB_BATCH")) {
     long long v = std::atoll(e);
@@ -407,7 +461,7 @@ static size_t batch_capacity(size_t have /* capacity of the queues the device po
   if (have >= nb) return nb;
   size_t free_b = 0, total_b = 0;
   if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-    const size_t per_path = (size_t)(1 + NUM_MAT_KINDS) * 3 * sizeof(Vec4<float>) + 8;  // ray + hit queues
+    const size_t per_path = (size_t)(1 + NUM_MAT_KINDS) * 3 * vec4_bytes + 8;  // ray + hit queues
     free_b += have * per_path;  // growing frees the old queues first
     while (nb > have && nb > ((size_t)1 << 20) && nb * per_path > free_b / 10 * 6) nb >>= 1;
   }
@@ -428,7 +482,7 @@ static int render_impl(ptb_scene *s, const ptb_params &p, R *d_sums, cudaStream_
   RenderConst rcst;
   if ((rc = fill_render_const(p, pl->npix, &rcst))) return rc;
   const long long total = (long long)pl->npix * p.samples_per_pixel;
-  const size_t NB = std::min<size_t>(batch_capacity(pl->work<R>().cap), (size_t)std::max<long long>(total, 1));
+  const size_t NB = std::min<size_t>(batch_capacity(pl->work<R>().cap, sizeof(Vec4<R>)), (size_t)std::max<long long>(total, 1));
   if ((rc = ensure_work<R>(pl, NB))) return rc;
   Work<R> &w = pl->work<R>();
   Ctl *ctl = pl->ctl;
@@ -437,10 +491,33 @@ static int render_impl(ptb_scene *s, const ptb_params &p, R *d_sums, cudaStream_
   TraceLaunch tl;
   if ((rc = trace_config<R, 0>(d, sc, scene_bytes, &tl))) return rc;
   const bool profile = (p.flags & PTB_FLAG_PROFILE) != 0;
+  // every event of this call, destroyed on every way out (the CK early returns included)
+  struct Events {
+    std::vector<cudaEvent_t> all;
+    ~Events() {
+      for (cudaEvent_t e : all) cudaEventDestroy(e);
+    }
+    int make(cudaEvent_t *e) {
+      CK(cudaEventCreate(e));
+      all.push_back(*e);
+      return PTB_OK;
+    }
+  } events;
   std::vector<cudaEvent_t> tev;
   cudaEvent_t e0, e1;
-  CK(cudaEventCreate(&e0));
-  CK(cudaEventCreate(&e1));
+  if ((rc = events.make(&e0)) || (rc = events.make(&e1))) return rc;
+  // PTB_FLAG_PROFILE: one pair of events per traversal launch, created before the timed region starts
+  const size_t n_batches = (size_t)((total + (long long)NB - 1) / (long long)NB);
+  if (profile) {
+    tev.resize(2 * n_batches * (size_t)std::max(p.max_bounces, 0));
+    for (cudaEvent_t &e : tev)
+      if ((rc = events.make(&e))) return rc;
+  }
+  size_t tev_next = 0;
+  pl->progress_total = (unsigned long long)total;
+  *pl->progress_host = 0ull;
+  // a scene with emitters collects their emission in k_shade, also after the last allowed intersection
+  const bool emissive = sc.has_emissive != 0;
   CK(cudaMemsetAsync(ctl, 0, sizeof(Ctl), st));
   CK(cudaEventRecord(e0, st));
   uint64_t launches = 0;
@@ -460,34 +537,32 @@ static int render_impl(ptb_scene *s, const ptb_params &p, R *d_sums, cudaStream_
   const int shade_grid0 = d->sm_count * std::max(shade_per_sm0, 1);
   for (long long first = 0; first < total; first += (long long)NB) {
     const unsigned n = (unsigned)std::min<long long>((long long)NB, total - first);
-    k_batch_ctl<<<1, 128, 0, st>>>(ctl, n, p.max_bounces);
+    k_batch_ctl<<<1, 128, 0, st>>>(ctl, n, p.max_bounces, pl->progress_dev, (unsigned long long)first);
     const int pass0 = (int)(first / pl->npix), i0 = (int)(first % pl->npix);
     const GenConst gen = make_gen(rcst, pl->pixel_list, pass0, i0);  // bounce 0 generates its own camera rays
     launches += 1;
     for (int b = 0; b < p.max_bounces; ++b) {
       const bool last = (b == p.max_bounces - 1);
       if (profile) {
-        cudaEvent_t a, z;
-        CK(cudaEventCreate(&a));
-        CK(cudaEventCreate(&z));
-        CK(cudaEventRecord(a, st));
-        tev.push_back(a);
-        tev.push_back(z);
+        CK(cudaEventRecord(tev[tev_next], st));
       }
       launch_trace<R, 0>(tl, st, sc, b == 0 ? &gen : nullptr, n, w.rays, &ctl->nseg_rays[b], 0u, &ctl->cursor[b], w.mq,
-                         (unsigned)w.slots, &ctl->nseg_mat[b][0], &ctl->n_rays[b], last ? 0 : 1, d_sums, R(0), R(0), nullptr, nullptr);
-      if (profile) CK(cudaEventRecord(tev.back(), st));
+                         (unsigned)w.slots, &ctl->nseg_mat[b][0], &ctl->n_rays[b], (last && !emissive) ? 0 : 1, d_sums, R(0), R(0), nullptr, nullptr);
+      if (profile) {
+        CK(cudaEventRecord(tev[tev_next + 1], st));
+        tev_next += 2;
+      }
       ++launches;
-      if (!last) {
-        // a path that is still alive after the last allowed bounce contributes black
-        // (integrator.ml:31-32), so the last bounce needs no scatter
+      if (!last || emissive) {
+        // a path that is still alive after the last allowed bounce contributes black (integrator.ml:31-32), so the
+        // last bounce needs no scatter — unless the scene has emitters, whose emission k_shade collects (last = 1)
         k_shade<R><<<(b == 0 && n >= (1u << 24)) ? shade_grid0 : shade_grid, 256, shade_smem, st>>>(sc, rcst, b, w.mq, (unsigned)w.slots, &ctl->nseg_mat[b][0], w.rays,
-                                               &ctl->nseg_rays[b + 1]);
+                                               &ctl->nseg_rays[b + 1], d_sums, last ? 1 : 0);
         ++launches;
       }
     }
   }
-  k_batch_ctl<<<1, 128, 0, st>>>(ctl, 0u, p.max_bounces);
+  k_batch_ctl<<<1, 128, 0, st>>>(ctl, 0u, p.max_bounces, pl->progress_dev, (unsigned long long)total);
   ++launches;
   CK(cudaEventRecord(e1, st));
   CK(cudaGetLastError());
@@ -520,9 +595,6 @@ static int render_impl(ptb_scene *s, const ptb_params &p, R *d_sums, cudaStream_
       }
     }
   }
-  for (cudaEvent_t e : tev) cudaEventDestroy(e);
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
   return PTB_OK;
 }
 
@@ -571,6 +643,10 @@ static int render_host_impl(ptb_scene *s, const ptb_params &p, double *image, pt
   return rc;
 }
 
+// which of the per-material hit queues a hit on this kind of material goes to: emissive hits (extension) travel
+// in the Lambertian queue, k_shade tells them apart by the material record it loads anyway
+static uint8_t queue_kind(int kind) { return (uint8_t)(kind == PTB_MAT_EMISSIVE ? PTB_MAT_LAMBERTIAN : kind); }
+
 static DMat make_dmat(const HostScene &h, size_t i) {
   DMat m;
   m.kind = h.mat[i].kind, m.tex = h.mat[i].texture, m.index = h.mat[i].index;
@@ -582,21 +658,42 @@ static DMat make_dmat(const HostScene &h, size_t i) {
   return m;
 }
 
+// per-device one-time setup: cached properties, the control block, the progress word
+static int ensure_pool(DevicePool *pl, int device) {
+  if (pl->sm_count == 0) {
+    int sms = 0, optin = 0;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    pl->sm_count = sms, pl->smem_optin = (size_t)optin;
+  }
+  if (!pl->ctl) {
+    CK(cudaMalloc((void **)&pl->ctl, sizeof(Ctl)));
+    CK(cudaMemset(pl->ctl, 0, sizeof(Ctl)));
+  }
+  if (!pl->progress_host) {
+    CK(cudaHostAlloc((void **)&pl->progress_host, sizeof(unsigned long long), cudaHostAllocMapped));
+    *pl->progress_host = 0;
+    CK(cudaHostGetDevicePointer((void **)&pl->progress_dev, pl->progress_host, 0));
+  }
+  return PTB_OK;
+}
+// a DeviceState for `s` on `device`: the one it already has there (tables released, object kept) or a new one
 static int new_device_state(ptb_scene *s, int device) {
   int rc = check_device(device);
   if (rc) return rc;
-  DeviceState *d = new DeviceState();
-  s->dev = d;
-  d->device = device;
-  cudaDeviceProp prop;
-  CK(cudaGetDeviceProperties(&prop, device));
-  d->sm_count = prop.multiProcessorCount;
-  d->smem_optin = prop.sharedMemPerBlockOptin;
-  d->pool = pool_for(device);
-  if (!d->pool->ctl) {
-    CK(cudaMalloc((void **)&d->pool->ctl, sizeof(Ctl)));
-    CK(cudaMemset(d->pool->ctl, 0, sizeof(Ctl)));
+  DevicePool *pl = pool_for(device);
+  if ((rc = ensure_pool(pl, device))) return rc;
+  if (s->dev && s->dev->device == device) {
+    release_device_tables(s->dev);
+  } else {
+    if (s->dev) destroy_device_state(s->dev);
+    s->dev = new DeviceState();
   }
+  DeviceState *d = s->dev;
+  d->device = device;
+  d->sm_count = pl->sm_count;
+  d->smem_optin = pl->smem_optin;
+  d->pool = pl;
   return PTB_OK;
 }
 
@@ -671,7 +768,7 @@ static int gpu_build_mesh(ptb_scene *s) {
     return PTB_OK;
   };
   std::vector<uint8_t> mk(h.mat.size());
-  for (size_t i = 0; i < mk.size(); ++i) mk[i] = (uint8_t)h.mat[i].kind;
+  for (size_t i = 0; i < mk.size(); ++i) mk[i] = queue_kind(h.mat[i].kind);
   G(H2D(vx, h.vx.data(), nv * 8)) G(H2D(vy, h.vy.data(), nv * 8)) G(H2D(vz, h.vz.data(), nv * 8))
   G(H2D(idx, h.tidx.data(), 3 * (size_t)n * 4)) G(H2D(tmat, h.tmat.data(), (size_t)n * 4)) G(H2D(tuv, h.tuv.data(), 6 * (size_t)n * 8))
   G(H2D(mkind, mk.data(), mk.size()))
@@ -771,9 +868,7 @@ static int gpu_build_mesh(ptb_scene *s) {
   const int n_wide = hc[0];
   // outputs
   Tables<float> &t = d->tf;
-  free_tables(t);
-  tbl_free(d->sphere_id), tbl_free(d->tri_id), tbl_free(d->sphere_mat), tbl_free(d->tri_mat), tbl_free(d->mats), tbl_free(d->prim_kind);
-  d->sphere_id = d->tri_id = d->sphere_mat = d->tri_mat = nullptr, d->mats = nullptr, d->prim_kind = nullptr;
+  release_device_tables(d);
   auto OUT = [&](auto **p, size_t count_) -> int {
     CK(tbl_alloc((void **)p, std::max<size_t>(count_, 1) * sizeof(**p)));
     return PTB_OK;
@@ -831,6 +926,7 @@ int ptb_device_count(void) {
 int ptb_scene_commit(ptb_scene *s, int32_t device, double *ms) {
   using clk = std::chrono::steady_clock;
   if (!s) return fail(PTB_E_INVALID, "commit: null scene");
+  s->committed = false;  // until every table is on the device (a failed re-commit must not leave a usable-looking scene)
   const HostScene &h = s->host;
   // Shape_tree.create: `failwith "expected non-empty list of shapes"` (shape_tree.ml:254-255)
   if (h.n_spheres() + h.n_tris() == 0) return fail(PTB_E_INVALID, "commit: expected non-empty list of shapes");
@@ -846,19 +942,23 @@ int ptb_scene_commit(ptb_scene *s, int32_t device, double *ms) {
       return fail(PTB_E_INVALID, "commit: texture row out of range");
   int rc = check_device(device);
   if (rc) return rc;
+  PoolLock lk(pool_for(device)->mu);
   auto t0 = clk::now();
   for (ptb_scene *r : s->replicas) ptb_scene_destroy(r);  // replicas of an older commit
   s->replicas.clear();
   s->bvh = WideBVH();
-  bool built = false;
-  if (want_gpu_builder(h)) {  // big pure-triangle mesh: build the tree on the device
+  auto drop_state = [&]() {  // a commit that failed half way leaves no device state behind
     if (s->dev) destroy_device_state(s->dev);
     s->dev = nullptr;
+  };
+  if (want_gpu_builder(h)) {  // big pure-triangle mesh: build the tree on the device
     if ((rc = new_device_state(s, device))) return rc;
     rc = gpu_build_mesh(s);
-    if (rc < 0) return rc;
-    built = rc == PTB_OK;
-    if (built) {
+    if (rc < 0) {
+      drop_state();
+      return rc;
+    }
+    if (rc == PTB_OK) {
       s->committed = true;
       if (ms) *ms = std::chrono::duration<double, std::milli>(clk::now() - t0).count();
       return PTB_OK;
@@ -868,37 +968,76 @@ int ptb_scene_commit(ptb_scene *s, int32_t device, double *ms) {
   // the traversal stack holds the tree's exact worst case + the sentinel; refuse trees it cannot hold rather
   // than dropping pushes on the device
   if (s->bvh.max_stack + 1 > 97) return fail(PTB_E_INVALID, "commit: tree too deep for the device traversal stack");
-  if ((rc = upload_scene(s, device))) return rc;
+  if ((rc = upload_scene(s, device))) {
+    drop_state();
+    return rc;
+  }
   if (ms) *ms = std::chrono::duration<double, std::milli>(clk::now() - t0).count();
   return PTB_OK;
 }
 
-/* the device half of a commit: tables and tree of `s` (already built) onto `device` */
+/* The device half of a commit: ids, materials, tree and float tables of `s` (already built) onto `device` as ONE
+ * block — written into pinned staging, copied with one cudaMemcpyAsync into one allocation.  (A dozen blocking
+ * cudaMemcpy's of pageable vectors cost 3.5 - 230 ms per commit of a 54 KB scene next to 50 GB of queues.) */
 static int upload_scene(ptb_scene *s, int32_t device) {
   const HostScene &h = s->host;
-  int rc = check_device(device);
+  s->committed = false;
+  int rc = new_device_state(s, device);
   if (rc) return rc;
-  if (s->dev) destroy_device_state(s->dev);
-  s->dev = nullptr;
-  if ((rc = new_device_state(s, device))) return rc;
   DeviceState *d = s->dev;
-  std::vector<int32_t> smat(s->bvh.sphere_order.size()), tmat(s->bvh.tri_order.size());
-  for (size_t k = 0; k < smat.size(); ++k) smat[k] = h.smat[s->bvh.sphere_order[k]];
-  for (size_t k = 0; k < tmat.size(); ++k) tmat[k] = h.tmat[s->bvh.tri_order[k]];
+  DevicePool *pl = d->pool;
+  PoolLock lk(pl->mu);
+  const size_t nS = s->bvh.sphere_order.size(), nT = s->bvh.tri_order.size();
+  std::vector<int32_t> smat(nS), tmat(nT);
+  for (size_t k = 0; k < nS; ++k) smat[k] = h.smat[s->bvh.sphere_order[k]];
+  for (size_t k = 0; k < nT; ++k) tmat[k] = h.tmat[s->bvh.tri_order[k]];
   std::vector<DMat> mats(h.mat.size());
   for (size_t i = 0; i < mats.size(); ++i) mats[i] = make_dmat(h, i);
-  if ((rc = upload(&d->sphere_id, s->bvh.sphere_order))) return rc;
-  if ((rc = upload(&d->tri_id, s->bvh.tri_order))) return rc;
-  if ((rc = upload(&d->sphere_mat, smat))) return rc;
-  if ((rc = upload(&d->tri_mat, tmat))) return rc;
-  if ((rc = upload(&d->mats, mats))) return rc;
-  std::vector<uint8_t> kinds(((smat.size() + tmat.size() + 15) / 16) * 16 + 16, 0);
-  for (size_t k = 0; k < smat.size(); ++k) kinds[k] = (uint8_t)h.mat[smat[k]].kind;
-  for (size_t k = 0; k < tmat.size(); ++k) kinds[smat.size() + k] = (uint8_t)h.mat[tmat[k]].kind;
-  if ((rc = upload(&d->prim_kind, kinds))) return rc;
+  std::vector<uint8_t> kinds(((nS + nT + 15) / 16) * 16 + 16, 0);
+  for (size_t k = 0; k < nS; ++k) kinds[k] = queue_kind(h.mat[smat[k]].kind);
+  for (size_t k = 0; k < nT; ++k) kinds[nS + k] = queue_kind(h.mat[tmat[k]].kind);
+  HostTables<float> ht;
+  make_host_tables<float>(s, &ht);
+  // layout of the block: 256-byte aligned slices
+  struct Slice {
+    const void *src;
+    size_t bytes, off;
+  };
+  Slice sl[11] = {{s->bvh.sphere_order.data(), nS * 4, 0}, {s->bvh.tri_order.data(), nT * 4, 0},
+                  {smat.data(), nS * 4, 0},               {tmat.data(), nT * 4, 0},
+                  {mats.data(), mats.size() * sizeof(DMat), 0}, {kinds.data(), kinds.size(), 0},
+                  {ht.nodes.data(), ht.nodes.size() * sizeof(Node4<float>), 0},
+                  {ht.sph.data(), ht.sph.size() * sizeof(Vec4<float>), 0},
+                  {ht.tri.data(), ht.tri.size() * sizeof(Vec4<float>), 0},
+                  {ht.uv.data(), ht.uv.size() * sizeof(float), 0},
+                  {ht.texs.data(), ht.texs.size() * sizeof(DTex<float>), 0}};
+  size_t total = 0;
+  for (Slice &x : sl) {
+    x.off = total;
+    total += (std::max<size_t>(x.bytes, 16) + 255) / 256 * 256;
+  }
+  if (pl->stage_cap < total) {
+    if (pl->stage_host) cudaFreeHost(pl->stage_host);
+    pl->stage_host = nullptr, pl->stage_cap = 0;
+    CK(cudaHostAlloc(&pl->stage_host, total + total / 2, cudaHostAllocDefault));
+    pl->stage_cap = total + total / 2;
+  }
+  char *hb = (char *)pl->stage_host;
+  for (const Slice &x : sl)
+    if (x.bytes) std::memcpy(hb + x.off, x.src, x.bytes);
+  CK(tbl_alloc(&d->blob, total));
+  CK(cudaMemcpyAsync(d->blob, hb, total, cudaMemcpyHostToDevice, 0));
+  char *db = (char *)d->blob;
+  d->sphere_id = (int32_t *)(db + sl[0].off), d->tri_id = (int32_t *)(db + sl[1].off);
+  d->sphere_mat = (int32_t *)(db + sl[2].off), d->tri_mat = (int32_t *)(db + sl[3].off);
+  d->mats = (DMat *)(db + sl[4].off), d->prim_kind = (uint8_t *)(db + sl[5].off);
+  d->ids_in_blob = true;
+  Tables<float> &t = d->tf;
+  t.nodes = (Node4<float> *)(db + sl[6].off), t.spheres = (Vec4<float> *)(db + sl[7].off);
+  t.tris = (Vec4<float> *)(db + sl[8].off), t.tri_uv = (float *)(db + sl[9].off), t.texs = (DTex<float> *)(db + sl[10].off);
+  t.in_blob = true, t.ready = true;
+  CK(cudaStreamSynchronize(0));  // the staging block may be reused by the next commit
   s->committed = true;
-  if ((rc = ensure_tables<float>(s))) return rc;
-  CK(cudaDeviceSynchronize());
   return PTB_OK;
 }
 
@@ -952,6 +1091,7 @@ int ptb_render_multi(ptb_scene *s, const ptb_params *p, int32_t n_devices, doubl
       int rc = check_device(i);
       if (rc) return rc;
       DevicePool *pl = sc->dev->pool;
+      PoolLock lk(pl->mu);
       if (pl->sums_cap < n3 * sizeof(float)) {
         cudaFree(pl->sums_buf);
         pl->sums_buf = nullptr, pl->sums_cap = 0;
@@ -978,6 +1118,7 @@ int ptb_render_multi(ptb_scene *s, const ptb_params *p, int32_t n_devices, doubl
   int rc = check_device(0);
   if (rc) return rc;
   DevicePool *pl0 = s->dev->pool;
+  PoolLock lk0(pl0->mu);
   PeerPtrs pp;
   std::memset(&pp, 0, sizeof pp);
   float *stage = nullptr;
@@ -995,11 +1136,11 @@ int ptb_render_multi(ptb_scene *s, const ptb_params *p, int32_t n_devices, doubl
       PeerPtrs one_src;
       std::memset(&one_src, 0, sizeof one_src);
       one_src.src[0] = stage, one_src.n = 1;
-      k_reduce_peers<<<(unsigned)((n3 / 4 + 255) / 256), 256>>>(sums[0], one_src, n3);
+      k_reduce_peers<<<(unsigned)(((n3 + 3) / 4 + 255) / 256), 256>>>(sums[0], one_src, n3);
       CK(cudaDeviceSynchronize());
     }
   }
-  if (pp.n) k_reduce_peers<<<(unsigned)((n3 / 4 + 255) / 256), 256>>>(sums[0], pp, n3);
+  if (pp.n) k_reduce_peers<<<(unsigned)(((n3 + 3) / 4 + 255) / 256), 256>>>(sums[0], pp, n3);
   CK(cudaGetLastError());
   if (stage) cudaFree(stage);
   if (pl0->img_cap < n3 * sizeof(double)) {
@@ -1050,6 +1191,7 @@ int ptb_render(ptb_scene *s, const ptb_params *p, double *image, ptb_stats *stat
   if (!p || !image) return fail(PTB_E_INVALID, "render: null argument");
   int rc = require_committed(s, p->device);
   if (rc) return rc;
+  PoolLock lk(s->dev->pool->mu);
   if (stats) std::memset(stats, 0, sizeof *stats);
   auto t0 = clk::now();
   rc = (p->flags & PTB_FLAG_F64) ? render_host_impl<double>(s, *p, image, stats)
@@ -1058,12 +1200,35 @@ int ptb_render(ptb_scene *s, const ptb_params *p, double *image, ptb_stats *stat
   return rc;
 }
 
+int ptb_render_progress(int32_t device, uint64_t *paths_done, uint64_t *paths_total) {
+  if (device < 0 || device >= 64) return fail(PTB_E_INVALID, "render_progress: device ordinal out of range");
+  const DevicePool *pl = pool_for(device);  // no lock: this is what another thread polls while a render holds it
+  const volatile unsigned long long *w = pl->progress_host;
+  if (paths_done) *paths_done = w ? (uint64_t)*w : 0u;
+  if (paths_total) *paths_total = (uint64_t)pl->progress_total;
+  return PTB_OK;
+}
+
+void *ptb_host_alloc(uint64_t bytes) {
+  void *p = nullptr;
+  cudaError_t e = cudaHostAlloc(&p, (size_t)std::max<uint64_t>(bytes, 1), cudaHostAllocDefault);
+  if (e != cudaSuccess) {
+    fail(PTB_E_CUDA, std::string("host_alloc: ") + cudaGetErrorString(e));
+    return nullptr;
+  }
+  return p;
+}
+void ptb_host_free(void *p) {
+  if (p) cudaFreeHost(p);
+}
+
 int ptb_render_device(ptb_scene *s, const ptb_params *p, float *d_sums, void *stream, ptb_stats *stats) {
   using clk = std::chrono::steady_clock;
   if (!p || !d_sums) return fail(PTB_E_INVALID, "render_device: null argument");
   if (p->flags & PTB_FLAG_F64) return fail(PTB_E_INVALID, "render_device: float32 sums only");
   int rc = require_committed(s, p->device);
   if (rc) return rc;
+  PoolLock lk(s->dev->pool->mu);
   if (stats) std::memset(stats, 0, sizeof *stats);
   auto t0 = clk::now();
   rc = render_impl<float>(s, *p, d_sums, (cudaStream_t)stream, stats);
@@ -1087,8 +1252,9 @@ int ptb_intersect_batch_device(ptb_scene *s, const float *d_o, const float *d_d,
   if (rc) return rc;
   DeviceState *d = s->dev;
   DevicePool *pl = d->pool;
+  PoolLock lk(pl->mu);
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t cap = std::min<size_t>(batch_capacity(pl->work<float>().cap), (size_t)std::max<int64_t>(n, 1));
+  const size_t cap = std::min<size_t>(batch_capacity(pl->work<float>().cap, sizeof(Vec4<float>)), (size_t)std::max<int64_t>(n, 1));
   if ((rc = ensure_work<float>(pl, cap))) return rc;
   Work<float> &w = pl->work<float>();
   size_t scene_bytes = 0;
@@ -1124,17 +1290,28 @@ int ptb_intersect_batch_device(ptb_scene *s, const float *d_o, const float *d_d,
   return PTB_OK;
 }
 
+/* Host buffers.  The rays are cut into chunks; chunk k+1 is copied to the device and chunk k-1's results come back
+ * while chunk k is traced (two streams, two sets of device staging buffers).  That only overlaps when the copies are
+ * real DMA transfers, i.e. from page-locked memory: buffers from ptb_host_alloc (or any registered memory) go
+ * straight through; pageable buffers of a big call are pinned for its duration (cudaHostRegister), small calls
+ * take the driver's staged copy. */
 int ptb_intersect_batch(ptb_scene *s, const float *o, const float *dd, float t_min, float t_max, int64_t n,
                         float *t_hit, int32_t *prim, int32_t device, ptb_stats *stats) {
   using clk = std::chrono::steady_clock;
   if (!o || !dd || !t_hit || !prim || n < 0) return fail(PTB_E_INVALID, "intersect_batch: bad args");
   int rc = require_committed(s, device);
   if (rc) return rc;
+  DeviceState *d = s->dev;
+  DevicePool *pl = d->pool;
+  PoolLock lk(pl->mu);
   if (stats) std::memset(stats, 0, sizeof *stats);
   auto t0 = clk::now();
-  const size_t nn = (size_t)std::max<int64_t>(n, 1);
-  DevicePool *pl = s->dev->pool;  // device staging buffers are kept between calls (grow-only)
-  const size_t want[4] = {nn * 12, nn * 12, nn * 4, nn * 4};
+  size_t chunk = (size_t)1 << 22;  // rays per chunk: 96 MB in, 32 MB out
+  if (const char *e = std::getenv("PTB_BATCH_CHUNK")) chunk = (size_t)std::max<long long>(1024, std::atoll(e));
+  chunk = std::min<size_t>(chunk, (size_t)std::max<int64_t>(n, 1));
+  const int nbuf = (size_t)n > chunk ? 2 : 1;
+  // device staging: [buffer][origins, directions, t, prim], kept between calls (grow-only)
+  const size_t want[4] = {nbuf * chunk * 12, nbuf * chunk * 12, nbuf * chunk * 4, nbuf * chunk * 4};
   for (int k = 0; k < 4; ++k)
     if (pl->batch_cap[k] < want[k]) {
       cudaFree(pl->batch_buf[k]);
@@ -1142,24 +1319,87 @@ int ptb_intersect_batch(ptb_scene *s, const float *o, const float *dd, float t_m
       CK(cudaMalloc(&pl->batch_buf[k], want[k]));
       pl->batch_cap[k] = want[k];
     }
-  float *d_o = (float *)pl->batch_buf[0], *d_d = (float *)pl->batch_buf[1], *d_t = (float *)pl->batch_buf[2];
-  int32_t *d_p = (int32_t *)pl->batch_buf[3];
-  auto th = clk::now();
-  CK(cudaMemcpy(d_o, o, (size_t)n * 12, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(d_d, dd, (size_t)n * 12, cudaMemcpyHostToDevice));
-  double ms_h2d = std::chrono::duration<double, std::milli>(clk::now() - th).count();
-  rc = ptb_intersect_batch_device(s, d_o, d_d, t_min, t_max, n, d_t, d_p, device, nullptr, stats);
-  auto td = clk::now();
-  if (!rc) {
-    CK(cudaMemcpy(t_hit, d_t, (size_t)n * 4, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(prim, d_p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  if ((rc = ensure_work<float>(pl, chunk))) return rc;
+  Work<float> &w = pl->work<float>();
+  size_t scene_bytes = 0;
+  DScene<float> sc = make_dscene<float>(s, &scene_bytes);
+  TraceLaunch tl;
+  if ((rc = trace_config<float, 1>(d, sc, scene_bytes, &tl))) return rc;
+  // pin pageable caller buffers for the duration of a big call
+  struct Pin {
+    void *p = nullptr;
+    ~Pin() {
+      if (p) cudaHostUnregister(p);
+    }
+  } pins[4];
+  const void *hostp[4] = {o, dd, t_hit, prim};
+  const size_t hostb[4] = {(size_t)n * 12, (size_t)n * 12, (size_t)n * 4, (size_t)n * 4};
+  bool pin_env = true;
+  if (const char *e = std::getenv("PTB_BATCH_PIN")) pin_env = std::atoi(e) != 0;
+  if (nbuf == 2 && pin_env)
+    for (int k = 0; k < 4; ++k) {
+      cudaPointerAttributes at;
+      const bool known = cudaPointerGetAttributes(&at, hostp[k]) == cudaSuccess && at.type != cudaMemoryTypeUnregistered;
+      cudaGetLastError();
+      if (known) continue;  // already page-locked (ptb_host_alloc, torch pinned memory, ...)
+      if (cudaHostRegister(const_cast<void *>(hostp[k]), hostb[k], k < 2 ? cudaHostRegisterReadOnly : cudaHostRegisterDefault) == cudaSuccess)
+        pins[k].p = const_cast<void *>(hostp[k]);
+      else if (cudaGetLastError(), cudaHostRegister(const_cast<void *>(hostp[k]), hostb[k], cudaHostRegisterDefault) == cudaSuccess)
+        pins[k].p = const_cast<void *>(hostp[k]);
+      else
+        cudaGetLastError();  // not fatal: that array takes the staged copy
+    }
+  struct Streams {
+    cudaStream_t st[2] = {nullptr, nullptr};
+    cudaEvent_t traced[2] = {nullptr, nullptr}, e0 = nullptr, e1 = nullptr;
+    ~Streams() {
+      for (int i = 0; i < 2; ++i) {
+        if (st[i]) cudaStreamDestroy(st[i]);
+        if (traced[i]) cudaEventDestroy(traced[i]);
+      }
+      if (e0) cudaEventDestroy(e0);
+      if (e1) cudaEventDestroy(e1);
+    }
+  } S;
+  for (int i = 0; i < nbuf; ++i) {
+    CK(cudaStreamCreateWithFlags(&S.st[i], cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&S.traced[i], cudaEventDisableTiming));
   }
+  CK(cudaEventCreate(&S.e0));
+  CK(cudaEventCreate(&S.e1));
+  CK(cudaDeviceSynchronize());  // the non-blocking streams below do not order against earlier default-stream work
+  CK(cudaEventRecord(S.e0, S.st[0]));
+  uint64_t launches = 0;
+  int64_t k = 0;
+  for (int64_t first = 0; first < n; first += (int64_t)chunk, ++k) {
+    const int b = (int)(k % nbuf);
+    const long long m = std::min<int64_t>((int64_t)chunk, n - first);
+    cudaStream_t st = S.st[b];
+    float *d_o = (float *)pl->batch_buf[0] + (size_t)b * chunk * 3, *d_d = (float *)pl->batch_buf[1] + (size_t)b * chunk * 3;
+    float *d_t = (float *)pl->batch_buf[2] + (size_t)b * chunk;
+    int32_t *d_p = (int32_t *)pl->batch_buf[3] + (size_t)b * chunk;
+    CK(cudaMemcpyAsync(d_o, o + 3 * first, (size_t)m * 12, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_d, dd + 3 * first, (size_t)m * 12, cudaMemcpyHostToDevice, st));
+    // the ray queue and the claim cursor are shared by the two streams: the kernels of chunk k wait for chunk k-1's
+    if (k > 0) CK(cudaStreamWaitEvent(st, S.traced[(k - 1) % nbuf], 0));
+    k_pack_rays<float><<<(unsigned)((m + 255) / 256), 256, 0, st>>>(d_o, d_d, m, w.rays);
+    CK(cudaMemsetAsync(&pl->ctl->cursor[MAX_BOUNCES], 0, sizeof(unsigned), st));
+    launch_trace<float, 1>(tl, st, sc, nullptr, 0u, w.rays, nullptr, (unsigned)((m + SEG - 1) / SEG),
+                           &pl->ctl->cursor[MAX_BOUNCES], w.mq, (unsigned)w.slots, nullptr, nullptr, 0, nullptr, t_min, t_max, d_t, d_p);
+    CK(cudaEventRecord(S.traced[b], st));
+    CK(cudaMemcpyAsync(t_hit + first, d_t, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(prim + first, d_p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+    launches += 2;
+  }
+  CK(cudaGetLastError());
+  for (int i = 0; i < nbuf; ++i) CK(cudaStreamSynchronize(S.st[i]));
   if (stats) {
-    stats->ms_h2d = ms_h2d;
-    stats->ms_d2h = std::chrono::duration<double, std::milli>(clk::now() - td).count();
+    stats->rays = (uint64_t)n;
+    stats->kernel_launches += launches;
     stats->h2d_bytes = (uint64_t)n * 24;
     stats->d2h_bytes = (uint64_t)n * 8;
     stats->ms_total = std::chrono::duration<double, std::milli>(clk::now() - t0).count();
+    stats->ms_device = stats->ms_total;  // copies and kernels overlap: the pipeline's time is the call's
   }
   return rc;
 }
@@ -1226,6 +1466,7 @@ int ptb_raygen(const ptb_params *p, int64_t first, int64_t n, int32_t *pixel, in
   int rc = check_device(p->device);
   if (rc) return rc;
   DevicePool &tmp = *pool_for(p->device);  // raygen needs no scene
+  PoolLock lk(tmp.mu);
   int world = p->tile_world > 0 ? p->tile_world : 1;
   if ((rc = ensure_pixel_list(&tmp, p->width, p->height, p->tile_rank, world))) return rc;
   RenderConst rcst;
@@ -1269,6 +1510,7 @@ int ptb_first_hit(ptb_scene *s, const ptb_params *p, float *t_hit, int32_t *prim
   if (rc) return rc;
   DeviceState *d = s->dev;
   DevicePool *pl = d->pool;
+  PoolLock lk(pl->mu);
   if ((rc = ensure_pixel_list(pl, p->width, p->height, 0, 1))) return rc;
   RenderConst rcst;
   if ((rc = fill_render_const(*p, pl->npix, &rcst))) return rc;

@@ -74,6 +74,14 @@ struct HostScene {
   std::vector<double> tuv;  // 6 per triangle
   int bg_kind = PTB_BG_GRADIENT_Y;
   double bg0[3] = {1, 1, 1}, bg1[3] = {0.5, 0.7, 1.0};
+  // extension (ptb_scene_set_light_quad): diffuse_plus_light = Mix (Diffuse, Quad_light)
+  bool has_light = false;
+  double light_o[3] = {0, 0, 0}, light_u[3] = {1, 0, 0}, light_v[3] = {0, 0, 1};
+  bool has_emissive() const {
+    for (const ptb_material &m : mat)
+      if (m.kind == PTB_MAT_EMISSIVE) return true;
+    return false;
+  }
   int64_t n_spheres() const { return (int64_t)sr.size(); }
   int64_t n_tris() const { return (int64_t)tidx.size() / 3; }
 };

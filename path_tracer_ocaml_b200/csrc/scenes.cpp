@@ -40,7 +40,7 @@ int ptb_scene_set_textures(ptb_scene *s, const ptb_texture *t, int32_t n) {
 int ptb_scene_set_materials(ptb_scene *s, const ptb_material *m, int32_t n) {
   if (!s || (n > 0 && !m) || n < 0) return fail(PTB_E_INVALID, "set_materials: bad args");
   for (int i = 0; i < n; ++i)
-    if (m[i].kind < PTB_MAT_LAMBERTIAN || m[i].kind > PTB_MAT_DIELECTRIC)
+    if (m[i].kind < PTB_MAT_LAMBERTIAN || m[i].kind > PTB_MAT_EMISSIVE)
       return fail(PTB_E_INVALID, "set_materials: unknown material kind");
   s->host.mat.assign(m, m + n);
   s->committed = false;
@@ -100,6 +100,29 @@ int ptb_scene_set_background(ptb_scene *s, int32_t kind, const double c0[3], con
   s->host.bg_kind = kind;
   for (int i = 0; i < 3; ++i) s->host.bg0[i] = c0[i], s->host.bg1[i] = c1 ? c1[i] : c0[i];
   s->committed = false;
+  return PTB_OK;
+}
+
+int ptb_scene_set_light_quad(ptb_scene *s, const double origin[3], const double u[3], const double v[3]) {
+  if (!s || (origin && (!u || !v))) return fail(PTB_E_INVALID, "set_light_quad: bad args");
+  HostScene &h = s->host;
+  h.has_light = origin != nullptr;
+  if (origin) {
+    const double nx = u[1] * v[2] - u[2] * v[1], ny = u[2] * v[0] - u[0] * v[2], nz = u[0] * v[1] - u[1] * v[0];
+    if (!(nx * nx + ny * ny + nz * nz > 0.0)) return fail(PTB_E_INVALID, "set_light_quad: degenerate quad");
+    for (int i = 0; i < 3; ++i) h.light_o[i] = origin[i], h.light_u[i] = u[i], h.light_v[i] = v[i];
+  }
+  s->committed = false;
+  return PTB_OK;
+}
+int ptb_scene_get_light_quad(const ptb_scene *s, int32_t *has_light, double origin[3], double u[3], double v[3]) {
+  if (!s) return fail(PTB_E_INVALID, "get_light_quad: null scene");
+  if (has_light) *has_light = s->host.has_light ? 1 : 0;
+  for (int i = 0; i < 3; ++i) {
+    if (origin) origin[i] = s->host.light_o[i];
+    if (u) u[i] = s->host.light_u[i];
+    if (v) v[i] = s->host.light_v[i];
+  }
   return PTB_OK;
 }
 
@@ -376,9 +399,9 @@ int ptb_scene_load_shirley(ptb_scene *s, double aspect, int32_t seed, double cam
   return PTB_OK;
 }
 
-int ptb_scene_load_cornell(ptb_scene *s, double aspect, int32_t background_kind, const double c0[3],
-                           const double c1[3], double cam[20]) {
-  if (!s || !cam || !c0) return fail(PTB_E_INVALID, "load_cornell: null argument");
+}  // extern "C"
+static int load_cornell_impl(ptb_scene *s, double aspect, int32_t background_kind, const double c0[3],
+                             const double c1[3], const double *radiance, double cam[20]) {
   clear_scene(s);
   SceneWriter w{s->host};
   // camera (main.ml:172-182)
@@ -444,8 +467,37 @@ int ptb_scene_load_cornell(ptb_scene *s, double aspect, int32_t background_kind,
   for (int i = 0; i < 3; ++i) s->ref_order.push_back(i);
   s->host.bg_kind = background_kind;
   for (int i = 0; i < 3; ++i) s->host.bg0[i] = c0[i], s->host.bg1[i] = c1 ? c1[i] : c0[i];
+  if (radiance) {
+    // EXTENSION (BASELINE.json configs[1] "diffuse+light sampling"): the reference's point
+    // light `light_pos` (main.ml:184-188; photons only) becomes a horizontal emissive square of the enclosure's
+    // cross-section at that height, and diffuse_plus_light mixes it with the cosine lobe
+    int em = w.material(PTB_MAT_EMISSIVE, w.solid(radiance[0], radiance[1], radiance[2]), 0.0);
+    std::vector<int> lq;
+    const D3 la = (lc - rx) - rz;
+    quad(em, la, rx * 2.0, rz * 2.0, &lq);
+    for (int t : lq) s->ref_order.push_back(~t);
+    // the light quad moves to camera space with the scene: origin as a point, edges as point differences
+    double px[3] = {la.x, la.x + 2 * r, la.x}, py[3] = {la.y, la.y, la.y}, pz[3] = {la.z, la.z, la.z + 2 * r};
+    ptb_camera_transform(cam + 4, px, py, pz, 3);
+    HostScene &h = s->host;
+    h.has_light = true;
+    h.light_o[0] = px[0], h.light_o[1] = py[0], h.light_o[2] = pz[0];
+    h.light_u[0] = px[1] - px[0], h.light_u[1] = py[1] - py[0], h.light_u[2] = pz[1] - pz[0];
+    h.light_v[0] = px[2] - px[0], h.light_v[1] = py[2] - py[0], h.light_v[2] = pz[2] - pz[0];
+  }
   transform_all(s, cam);  // main.ml:211-218
   return PTB_OK;
+}
+extern "C" {
+int ptb_scene_load_cornell(ptb_scene *s, double aspect, int32_t background_kind, const double c0[3],
+                           const double c1[3], double cam[20]) {
+  if (!s || !cam || !c0) return fail(PTB_E_INVALID, "load_cornell: null argument");
+  return load_cornell_impl(s, aspect, background_kind, c0, c1, nullptr, cam);
+}
+int ptb_scene_load_cornell_lit(ptb_scene *s, double aspect, const double radiance[3], double cam[20]) {
+  if (!s || !cam || !radiance) return fail(PTB_E_INVALID, "load_cornell_lit: null argument");
+  const double black[3] = {0, 0, 0};
+  return load_cornell_impl(s, aspect, PTB_BG_CONSTANT, black, black, radiance, cam);
 }
 
 int ptb_scene_load_mesh(ptb_scene *s, const float *xyz, int64_t nv, const int32_t *faces, int64_t nf,

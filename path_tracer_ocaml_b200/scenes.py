@@ -77,6 +77,14 @@ class Scene:
         b = None if c1 is None else np.asarray(c1, dtype=np.float64)
         check(lib().ptb_scene_set_background(self.h, kind, dptr(a), None if b is None else dptr(b)))
 
+    def set_light_quad(self, origin, u, v):
+        """Extension: diffuse_plus_light = Mix (Diffuse, Quad_light) (ptb200.h); origin=None removes the light."""
+        if origin is None:
+            check(lib().ptb_scene_set_light_quad(self.h, None, None, None))
+            return
+        o, a, b = (np.asarray(x, dtype=np.float64) for x in (origin, u, v))
+        check(lib().ptb_scene_set_light_quad(self.h, dptr(o), dptr(a), dptr(b)))
+
     def commit(self, device=0):
         ms = C.c_double(0)
         check(lib().ptb_scene_commit(self.h, device, C.byref(ms)))
@@ -120,6 +128,10 @@ class Scene:
         c0, c1 = np.zeros(3), np.zeros(3)
         check(L.ptb_scene_get_background(self.h, C.byref(kind), dptr(c0), dptr(c1)))
         t.update(bg_kind=kind.value, bg0=c0, bg1=c1)
+        has = C.c_int32()
+        lo, lu, lv = np.zeros(3), np.zeros(3), np.zeros(3)
+        check(L.ptb_scene_get_light_quad(self.h, C.byref(has), dptr(lo), dptr(lu), dptr(lv)))
+        t.update(has_light=bool(has.value), light_o=lo, light_u=lu, light_v=lv)
         n = L.ptb_scene_get_prim_order(self.h, None, 0)
         order = np.zeros(max(n, 1), dtype=np.int32)
         if n:
@@ -146,6 +158,17 @@ def cornell_box(width, height, background=("constant", (1.0, 1.0, 1.0), None)):
     c1 = None if background[2] is None else np.asarray(background[2], dtype=np.float64)
     check(lib().ptb_scene_load_cornell(s.h, width / height, kind, dptr(c0), None if c1 is None else dptr(c1),
                                        dptr(cam)))
+    s.camera = Camera(cam)
+    return s
+
+
+def cornell_box_lit(width, height, radiance=(32.0, 32.0, 32.0)):
+    """Extension (BASELINE.json configs[1] "diffuse+light sampling"): the cornell geometry in a closed black box,
+    lit by an emissive square at the reference's light position, sampled through the mixture pdf."""
+    s = Scene()
+    cam = np.zeros(20)
+    r = np.asarray(radiance, dtype=np.float64)
+    check(lib().ptb_scene_load_cornell_lit(s.h, width / height, dptr(r), dptr(cam)))
     s.camera = Camera(cam)
     return s
 
