@@ -14,7 +14,12 @@ shirley_spheres/bin/main.ml:264) and inside `e2e`.
 `--impl reference`: the reference renderer is OCaml 5 + Rust and cannot be built in this image, so this
 arm times oracle/ (kind "port": the C++ float64 restatement of the OCaml-domains + AVX path, AVX2
 intrinsics leaf kernel, N-1 worker threads + 1 stitcher like integrator.ml:137-151) on all host cores,
-on a bounded sample (the first passes) of the same workload.
+on a bounded sample (the first passes) of the same workload.  That arm is self-contained: it loads only
+oracle/ (liboracle.so + the committed scene file oracle/scenes/shirley_spheres.npz), never the product.
+
+N>1 (torchrun, one rank per GPU): tiles dealt round-robin; the only exchange is a reduce-scatter of the sums
+by row bands + a one-row halo swap, every rank resolves its own band, the bands are gathered on rank 0
+(path_tracer_ocaml_b200/distributed.py).  `ms_reduce` / `ms_resolve` / `ms_gather` time those phases.
 """
 import argparse
 import ctypes as C
@@ -89,20 +94,22 @@ class ClockSampler:
         return out
 
 
-def make_params(scene, w, h, spp, mb, rank=0, world=1, flags=0):
-    from path_tracer_ocaml_b200 import capi
-    c = scene.camera
-    return capi.Params(width=w, height=h, samples_per_pixel=spp, max_bounces=mb, lower_left_x=c.lower_left_x,
-                       lower_left_y=c.lower_left_y, view_x=c.view_x, view_y=c.view_y, tile_rank=rank,
-                       tile_world=world, flags=flags, device=0)
+def config_dict(world, spp):
+    """The `config` of BOTH arms (the reference arm runs a bounded sample of it, described in cpu_baseline.sample)."""
+    return {"workload": WORKLOAD if spp == SPP else f"DEV OVERRIDE spp={spp}: " + WORKLOAD,
+            "sharding": f"reference tile list (Tile.split 1024 px), tile t -> rank t mod {world}",
+            "l2": "no flush needed: each wavefront batch (up to 256 Mi paths) streams tens of GB of queue state (>> 126 MB L2)",
+            "paths_per_step": W * H * spp}
 
 
-def oracle_sample(scene, params, pass_limit, threads):
+def oracle_sample(spp, pass_limit, threads):
     """Times the oracle (CPU baseline, kind 'port') on the first `pass_limit` passes of the workload and
-    returns throughput + the reference-faithful per-ray test counts that define the algorithmic work."""
+    returns throughput + the reference-faithful per-ray test counts that define the algorithmic work.
+    Loads oracle/ only: the scene comes from oracle/scenes/shirley_spheres.npz."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import pyoracle as O
-    osc = O.OracleScene(scene.tables())
+    osc = O.OracleScene(O.load_scene_file("shirley_spheres"))
+    params = O.make_params(O.shirley_camera(W / H), W, H, spp, MB)
     t0 = time.perf_counter()
     _, cn = osc.render(params, n_threads=threads, pass_limit=pass_limit)
     dt = time.perf_counter() - t0
@@ -117,14 +124,11 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import path_tracer_ocaml_b200 as P
     cores = os.cpu_count() or 1
-    scene = P.shirley_spheres(W, H)
-    params = make_params(scene, W, H, SPP, MB)
     pass_limit = 4  # 33 M paths per step: a bounded sample of the 8.49 G-path workload
     vals = []
     for i in range(args.warmup + args.steps):
-        r = oracle_sample(scene, params, pass_limit, cores)
+        r = oracle_sample(SPP, pass_limit, cores)
         log(f"[reference] step {i}: {r['seconds']:.2f}s {r['mpaths']:.2f} Mpaths/s")
         if i >= args.warmup:
             vals.append(r)
@@ -137,7 +141,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "mrays_per_s": rays / sec / 1e6,
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / len(vals),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": sample},
+            "config": config_dict(args.gpus, SPP),
             "cpu_baseline": {"value": value, "unit": "Mpaths/s", "cores": cores, "kind": "port", "sample": sample,
                              "what": "C++ float64 restatement of the OCaml-domains+AVX path (oracle/), not the OCaml binary"},
             "e2e": {"value": value, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -162,12 +166,11 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
-    import numpy as np
     import torch
     import torch.distributed as dist
     import path_tracer_ocaml_b200 as P
     from path_tracer_ocaml_b200 import capi
-    from path_tracer_ocaml_b200.distributed import render_sharded
+    from path_tracer_ocaml_b200.distributed import SharedHostImage, alloc_padded_sums, render_sharded_bands
 
     spp = args.spp
     rank = int(os.environ.get("RANK", "0"))
@@ -184,27 +187,29 @@ def main():
 
     scene = P.shirley_spheres(W, H)
     integ = P.Integrator(scene, W, H, spp, MB, device=local, tile_rank=rank, tile_world=world)
-    sums = torch.zeros(H, W, 3, dtype=torch.float32, device=dev)
-    image = torch.empty_like(sums)
+    sums = alloc_padded_sums(H, W, world, dev)  # the first H rows are the frame
     launches = [0]
     acc = {"rays": 0, "ms_trace": 0.0, "ms_device": 0.0}
+    phase_ms = {"reduce": 0.0, "resolve": 0.0, "gather": 0.0}
+    out = {}
 
-    def step(profile):
+    def step(profile, gather_to=0):
+        """One render: this rank's tiles -> sums; reduce-scatter by row bands + halo swap; every rank resolves its
+        band; (gather_to = 0) the bands are gathered on rank 0's device."""
         sums.zero_()
+        integ.render_device(sums, flags=capi.PTB_FLAG_PROFILE if profile else 0)
+        launches[0] += integ.stats.kernel_launches + 1
+        acc["rays"] += integ.stats.rays
+        acc["ms_trace"] += integ.stats.ms_trace
+        acc["ms_device"] += integ.stats.ms_device
+        timers = {} if profile else None
 
-        def render_sums(r, n):
-            integ.render_device(sums, flags=capi.PTB_FLAG_PROFILE if profile else 0)
-            launches[0] += integ.stats.kernel_launches + 1
-            acc["rays"] += integ.stats.rays
-            acc["ms_trace"] += integ.stats.ms_trace
-            acc["ms_device"] += integ.stats.ms_device
-            return sums
-
-        def resolve(s):
+        def resolve_rows(loc):
             launches[0] += 1
-            return integ.resolve_device(s, out=image)
+            return integ.resolve_rows_device(loc)
 
-        render_sharded(render_sums, resolve)
+        out["band"], out["image"] = render_sharded_bands(sums, H, resolve_rows, gather_to=gather_to, timers=timers)
+        return timers
 
     def barrier():
         if world > 1:
@@ -220,20 +225,26 @@ def main():
     launches[0] = 0
     acc.update(rays=0, ms_trace=0.0, ms_device=0.0)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    all_timers = []
     barrier()
     e0.record()
     for _ in range(args.steps):
-        step(True)
+        all_timers.append(step(True))
     e1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
+    for tm in all_timers:  # (events are read after the closing synchronize)
+        for k, (a, z) in tm.items():
+            phase_ms[k] += a.elapsed_time(z)
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     stat = torch.tensor([float(acc["rays"]), float(launches[0])], device=dev, dtype=torch.float64)
     tr = torch.tensor([acc["ms_trace"]], device=dev, dtype=torch.float64)
+    ph = torch.tensor([phase_ms["reduce"], phase_ms["resolve"], phase_ms["gather"], acc["ms_device"]], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(stat, op=dist.ReduceOp.SUM)
         dist.all_reduce(tr, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ph, op=dist.ReduceOp.MAX)
     total_ms = ms.item()
     total_rays, total_launches, ms_trace = stat[0].item(), int(stat[1].item()), tr.item()
     timed = dict(acc)  # rank 0's counters of the timed region only (the e2e leg below keeps accumulating)
@@ -241,13 +252,15 @@ def main():
     value = paths_per_step * args.steps / (total_ms * 1e-3) / 1e6
     mrays = total_rays / (total_ms * 1e-3) / 1e6
 
-    # ---- e2e: through the public API with HOST buffers: scene commit (BVH build + upload of the tables),
-    # render, reduce, resolve, and the device->host read of the image, wall clock --------------------------
-    # N=1: the reference-facing C-ABI calls with HOST buffers: ptb_scene_commit (BVH build + host->device
-    # copy of the scene tables) + ptb_render (render, resolve, device->host copy of the float64 image the
-    # reference's Bimage holds).  N>1: commit + sharded render + NCCL reduce + resolve + image to pinned host.
+    # ---- e2e: through the public API with HOST buffers, wall clock, every step ---------------------------------
+    # N=1: the reference-facing C-ABI calls: ptb_scene_commit (BVH build + host->device copy of the scene tables) +
+    # ptb_render (render, resolve, device->host copy of the float64 image the reference's Bimage holds).
+    # N>1: commit + sharded render + band exchange + per-rank resolve, then every rank copies ITS band of the image
+    # into one page-locked host image shared by the ranks (each over its own PCIe link); the step ends when the whole
+    # image is in host memory (barrier).
     t = scene.tables()
     h2d = int(t["n_spheres"] * 5 * 8 + t["n_materials"] * 16 + t["n_textures"] * 48 + 256)
+    shared = None
     if world == 1:
         host_img = torch.empty(H, W, 3, dtype=torch.float64).pin_memory()
         host_np = host_img.numpy()
@@ -255,10 +268,12 @@ def main():
         e2e_what = ("ptb_scene_commit (BVH build + table upload) + ptb_render into a pinned host float64 image "
                     "(render + resolve + device->host copy), wall clock")
     else:
-        host_img = torch.empty(H, W, 3, dtype=torch.float32).pin_memory() if rank == 0 else None
+        shared = SharedHostImage(H, W, world, rank)
         d2h = int(W * H * 3 * 4)
-        e2e_what = ("scene commit (BVH build + table upload) + sharded render + NCCL reduce + resolve + image to "
-                    "pinned host memory, wall clock")
+        e2e_what = ("scene commit (BVH build + table upload) + sharded render + reduce-scatter by row bands + per-rank "
+                    "resolve + every rank's band copied into one shared page-locked host float32 image, wall clock "
+                    f"(d2h_bytes_per_step is the whole image; each rank moves 1/{world} of it)")
+
     def e2e_step():
         tc = time.perf_counter()
         scene.commit(local)  # host->device copy of the step's inputs (the scene tables), incl. BVH build
@@ -269,9 +284,9 @@ def main():
             log(f"e2e step: commit {1e3 * (tr - tc):.1f} ms, ptb_render {1e3 * (time.perf_counter() - tr):.1f} ms "
                 f"(device {integ.stats.ms_device:.1f} ms, d2h {integ.stats.ms_d2h:.1f} ms)")
         else:
-            step(False)
-            if rank == 0:
-                host_img.copy_(image, non_blocking=False)
+            step(False, gather_to=None)
+            shared.put_band(out["band"])
+            barrier()  # the image is complete in host memory when every rank's copy has landed
 
     n_launch_timed = launches[0]
     e2e_step()  # one untimed pass: the first host-buffer call grows the library's pooled device image buffers
@@ -283,6 +298,8 @@ def main():
     barrier()
     e2e_s = time.perf_counter() - t0
     e2e_val = paths_per_step * args.steps / e2e_s / 1e6
+    if shared is not None:
+        shared.close()
 
     if rank != 0:
         if world > 1:
@@ -296,16 +313,13 @@ def main():
     per_ray = None
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
-        r = oracle_sample(scene, make_params(scene, W, H, spp, MB), 4 if spp >= 4 else spp, cores)
+        r = oracle_sample(spp, 4 if spp >= 4 else spp, cores)
         per_ray = r["per_ray"]
         cpu = {"value": r["mpaths"], "unit": "Mpaths/s", "mrays_per_s": r["mrays"], "cores": cores, "kind": "port",
                "sample": f"first 4 of {spp} passes of the workload ({r['paths']} paths, {r['seconds']:.1f} s)",
                "what": "C++ float64 restatement of the OCaml-domains+AVX path (oracle/), not the OCaml binary"}
-    if per_ray is None:  # N>1: reuse the committed measurement of the same config (profiles/)
-        try:
-            per_ray = json.load(open(os.path.join(ROOT, "profiles", "algorithmic_work_c4.json")))["per_ray"]
-        except Exception:
-            per_ray = {"box": 21.3, "sphere": 4.9, "tri": 0.0, "rays_per_path": 2.56, "hits_per_path": 1.58}
+    if per_ray is None:  # N>1 (no CPU leg): the committed oracle counts of the same config — deterministic numbers
+        per_ray = json.load(open(os.path.join(ROOT, "profiles", "algorithmic_work_c4.json")))["per_ray"]
     a_trace = per_ray["box"] * C_BOX + per_ray["sphere"] * C_SPH + per_ray["tri"] * C_TRI
     c_gen = 40.0 + 5.0 * (2.0 + 2.0 * per_ray["hits_per_path"])
     a_ray = a_trace + C_HIT + (c_gen + C_FILM) / per_ray["rays_per_path"]
@@ -320,7 +334,8 @@ def main():
         batch = int(os.environ.get("PTB_BATCH", 1 << 28))                        # paths per wavefront batch
         n_trace_launches = args.steps * MB * -(-(paths_per_step // world) // batch)  # one k_trace per bounce per batch
         traffic = tk["dram_bytes_per_ray"] * rays_rank0 / n_trace_launches
-        traffic_note = tk.get("note")
+        traffic_note = ("STATIC, not measured in this run: DRAM bytes per ray of the committed `ncu --set full` capture "
+                        "(profiles/trace_kernel_ncu.json) x the rays of an average launch of this run. " + (tk.get("note") or ""))
     except Exception:
         pass
     hbm_peak = None
@@ -338,10 +353,7 @@ def main():
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32 (R2 sample stream and cx,cy in f64, bit-exact)", "data": "synthetic",
-        "config": {"workload": WORKLOAD if spp == SPP else f"DEV OVERRIDE spp={spp}: " + WORKLOAD,
-                   "sharding": f"reference tile list (Tile.split 1024 px), tile t -> rank t mod {world}",
-                   "l2": "no flush needed: each wavefront batch (up to 256 Mi paths) streams tens of GB of queue state (>> 126 MB L2)",
-                   "paths_per_step": paths_per_step},
+        "config": config_dict(world, spp),
         "roofline": {"bound": "fp32_issue", "kernel": "k_trace<float,0>", "achieved": trace_tlops, "peak": peak.value,
                      "unit": "Tlane-op/s", "frac": trace_tlops / peak.value, "traffic": traffic,
                      "traffic_note": traffic_note,
@@ -370,6 +382,11 @@ def main():
                 "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps, "what": e2e_what},
         "gpu_launches": total_launches,
         "clocks": clocks,
+        # the exchange after the render, max over ranks, per step (device events on the launching stream): reduce =
+        # reduce-scatter by row bands + halo rows, resolve = filter + gamma of the own band, gather = bands to rank 0;
+        # render = the wavefront pipeline itself
+        "exchange": {"ms_reduce": ph[0].item() / args.steps, "ms_resolve": ph[1].item() / args.steps,
+                     "ms_gather": ph[2].item() / args.steps, "ms_render_max_rank": ph[3].item() / args.steps},
     }
     _emit(json.dumps(line))
     if world > 1:

@@ -20,6 +20,7 @@ type material_row =
   | Lambertian of int (* texture row *)
   | Metal of int
   | Dielectric of float (* refractive index *)
+  | Emissive of int (* extension: Material.emit = this texture row, scatter = Absorb (ptb200.h) *)
 
 type background =
   | Constant of float * float * float
@@ -40,6 +41,10 @@ external set_triangles : scene -> f64array -> f64array -> f64array -> i32array -
 
 external set_background : scene -> background -> unit = "ptb_ml_set_background"
 
+(* extension: ~diffuse_plus_light = Mix (Diffuse, Quad_light {origin; u; v}) instead of Pdf.diffuse (render_command.ml:81) *)
+external set_light_quad :
+  scene -> (float * float * float) * (float * float * float) * (float * float * float) -> unit = "ptb_ml_set_light_quad"
+
 (* Shape_tree.create + upload; returns milliseconds, printed like "build time" (shirley main.ml:264) *)
 external commit : scene -> device:int -> float = "ptb_ml_commit"
 
@@ -48,6 +53,13 @@ external commit : scene -> device:int -> float = "ptb_ml_commit"
 external render :
   scene -> width:int -> height:int -> spp:int -> max_bounces:int -> camera:float * float * float * float
   -> device:int -> f64array -> float (* device ms *) = "ptb_ml_render_bc" "ptb_ml_render"
+
+(* `update_progress` (integrator.ml:130,150; render_command.ml:86-104) as a poll: (paths done, paths in total) of the
+   render in flight on [device].  Call it from another domain while [render] runs — the library serialises calls
+   that use the same device and never calls back into OCaml:
+     let d = Domain.spawn (fun () -> Ptb.render scene ... image) in
+     while not (finished ()) do let done_, total = Ptb.render_progress ~device:0 in report (done_ - !seen); ... done *)
+external render_progress : device:int -> int * int = "ptb_ml_render_progress"
 
 (* batched generalisation of spheres_intersect_native: t (nan = miss) and primitive index (-1 = miss) per ray *)
 external intersect_batch :

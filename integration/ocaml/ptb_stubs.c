@@ -58,7 +58,8 @@ CAMLprim value ptb_ml_set_textures(value s, value rows) {
   CAMLreturn(Val_unit);
 }
 
-/* material_row: Lambertian of int (tag 0) | Metal of int (tag 1) | Dielectric of float (tag 2) */
+/* material_row: Lambertian of int (tag 0) | Metal of int (tag 1) | Dielectric of float (tag 2) | Emissive of int (tag 3,
+   the extension of ptb200.h: Material.emit = the texture, scatter = Absorb) */
 CAMLprim value ptb_ml_set_materials(value s, value rows) {
   CAMLparam2(s, rows);
   mlsize_t n = Wosize_val(rows);
@@ -69,6 +70,7 @@ CAMLprim value ptb_ml_set_materials(value s, value rows) {
     switch (Tag_val(r)) {
       case 0: m[i].kind = PTB_MAT_LAMBERTIAN, m[i].texture = Int_val(Field(r, 0)), m[i].index = 1.0; break;
       case 1: m[i].kind = PTB_MAT_METAL, m[i].texture = Int_val(Field(r, 0)), m[i].index = 1.0; break;
+      case 3: m[i].kind = PTB_MAT_EMISSIVE, m[i].texture = Int_val(Field(r, 0)), m[i].index = 1.0; break;
       default: m[i].kind = PTB_MAT_DIELECTRIC, m[i].texture = -1, m[i].index = Double_val(Field(r, 0)); break;
     }
   }
@@ -111,6 +113,29 @@ CAMLprim value ptb_ml_set_background(value s, value bg) {
     check(ptb_scene_set_background(Scene_val(s), PTB_BG_GRADIENT_Y, c0, c1));
   }
   CAMLreturn(Val_unit);
+}
+
+/* light quad: (origin, u, v), three float triples (extension: ~diffuse_plus_light = Mix (Diffuse, Quad_light)) */
+CAMLprim value ptb_ml_set_light_quad(value s, value quad) {
+  CAMLparam2(s, quad);
+  double o[3], u[3], v[3];
+  for (int c = 0; c < 3; ++c)
+    o[c] = Double_val(Field(Field(quad, 0), c)), u[c] = Double_val(Field(Field(quad, 1), c)), v[c] = Double_val(Field(Field(quad, 2), c));
+  check(ptb_scene_set_light_quad(Scene_val(s), o, u, v));
+  CAMLreturn(Val_unit);
+}
+
+/* update_progress (integrator.ml:130,150) as a poll: (paths done, paths in total) of the render in flight on `device`.
+   Cheap and lock-free: meant to be called from another domain while ptb_ml_render has the runtime lock released. */
+CAMLprim value ptb_ml_render_progress(value device) {
+  CAMLparam1(device);
+  CAMLlocal1(pair);
+  uint64_t done = 0, total = 0;
+  check(ptb_render_progress(Int_val(device), &done, &total));
+  pair = caml_alloc(2, 0);
+  Store_field(pair, 0, Val_long((intnat)done));
+  Store_field(pair, 1, Val_long((intnat)total));
+  CAMLreturn(pair);
 }
 
 CAMLprim value ptb_ml_commit(value s, value device) {

@@ -158,7 +158,7 @@ class OracleScene:
     @staticmethod
     def params(product_params):
         p = Params()
-        C.memmove(C.byref(p), C.byref(product_params), C.sizeof(Params))
+        C.memmove(C.byref(p), C.byref(product_params), C.sizeof(Params))  # same POD layout (ptb_params)
         return p
 
     def render(self, params, n_threads=1, pass_limit=0, flags=None):
@@ -210,3 +210,38 @@ class OracleScene:
         n = L.orc_scene_leaf_histogram(self.h, iptr(sizes), iptr(counts), 64)
         return {"depth": L.orc_scene_tree_depth(self.h), "nodes": L.orc_scene_node_count(self.h),
                 "leaf_histogram": {int(s): int(c) for s, c in zip(sizes[:n], counts[:n])}}
+
+
+# ---- scenes the oracle can load on its own (no product library) ----------------------------------------------------
+def load_scene_file(name):
+    """Tables of oracle/scenes/<name>.npz in the dict layout OracleScene takes (written by make_scene_files.py)."""
+    z = np.load(os.path.join(_HERE, "scenes", name + ".npz"))
+    nm, nt = len(z["mat_kind"]), len(z["tex_kind"])
+    mats, texs = (Material * max(nm, 1))(), (Texture * max(nt, 1))()
+    for i in range(nm):
+        mats[i].kind, mats[i].texture, mats[i].index = int(z["mat_kind"][i]), int(z["mat_texture"][i]), float(z["mat_index"][i])
+    for i in range(nt):
+        texs[i].kind = int(z["tex_kind"][i])
+        texs[i].width, texs[i].height, texs[i].even, texs[i].odd = (int(v) for v in z["tex_whe"][i])
+        for c in range(3):
+            texs[i].rgb[c] = float(z["tex_rgb"][i][c])
+    e = np.zeros(0)
+    return {"n_spheres": len(z["rs"]), "n_vertices": 0, "n_triangles": 0, "xs": z["xs"], "ys": z["ys"], "zs": z["zs"],
+            "rs": z["rs"], "sphere_material": z["sphere_material"], "vx": e, "vy": e, "vz": e, "uv": e,
+            "indices": np.zeros(0, dtype=np.int32), "tri_material": np.zeros(0, dtype=np.int32),
+            "materials": mats, "n_materials": nm, "textures": texs, "n_textures": nt,
+            "bg_kind": int(z["bg_kind"]), "bg0": z["bg0"], "bg1": z["bg1"], "prim_order": z["prim_order"]}
+
+
+def shirley_camera(aspect):
+    """Camera.create for shirley_spheres (main.ml:26-31) through the oracle's own restatement: (llx, lly, vx, vy)."""
+    out = np.zeros(20)
+    lib().orc_camera_create(dptr(d3([13.0, 2.0, 4.5])), dptr(d3([0.0, 0.0, 0.0])), dptr(d3([0.0, 1.0, 0.0])), float(aspect),
+                            20.0, dptr(out))
+    return tuple(float(v) for v in out[:4])
+
+
+def make_params(cam4, width, height, spp, max_bounces, rank=0, world=1, flags=0):
+    return Params(width=width, height=height, samples_per_pixel=spp, max_bounces=max_bounces, lower_left_x=cam4[0],
+                  lower_left_y=cam4[1], view_x=cam4[2], view_y=cam4[3], tile_rank=rank, tile_world=world, flags=flags,
+                  device=0)

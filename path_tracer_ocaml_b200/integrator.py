@@ -85,6 +85,18 @@ class Integrator:
                                        p.samples_per_pixel, flags, p.device, C.c_void_p(st.cuda_stream)))
         return out
 
+    def resolve_rows_device(self, local, out=None, flags=0, stream=None):
+        """Filter + gamma of a block of summed rows (rows, W, 3) — a band of the frame with its halo rows — as an
+        image of that height: what each rank runs on its own band after the reduce-scatter (distributed.py)."""
+        import torch
+        p = self.params
+        if out is None:
+            out = torch.empty_like(local)
+        st = torch.cuda.current_stream(local.device) if stream is None else stream
+        check(lib().ptb_resolve_device(C.c_void_p(local.data_ptr()), C.c_void_p(out.data_ptr()), p.width, local.shape[0],
+                                       p.samples_per_pixel, flags, p.device, C.c_void_p(st.cuda_stream)))
+        return out
+
     def first_hit(self):
         p = self._p(0)
         t = np.empty((p.height, p.width), dtype=np.float32)

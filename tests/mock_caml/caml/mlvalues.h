@@ -18,6 +18,9 @@ typedef uintptr_t header_t;
 #define CAMLprim
 #define Val_int(x) ((value)(((intnat)(x) << 1) + 1))
 #define Int_val(v) ((int)((v) >> 1))
+#define Val_long(x) ((value)(((intnat)(x) << 1) + 1))
+#define Long_val(v) ((intnat)((v) >> 1))
+#define Store_field(b, i, v) (Field(b, i) = (v))
 #define Val_unit Val_int(0)
 #define Is_block(v) (((v)&1) == 0)
 #define Hd_val(v) (((header_t *)(v))[-1])

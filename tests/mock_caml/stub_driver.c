@@ -15,6 +15,7 @@
 #include <caml/memory.h>
 #include <caml/mlvalues.h>
 #include <caml/threads.h>
+#include "ptb200.h"
 
 jmp_buf mock_caml_handler;
 char mock_caml_exn[512];
@@ -30,6 +31,8 @@ value ptb_ml_set_background(value, value);
 value ptb_ml_commit(value, value);
 value ptb_ml_render_bc(value *, int);
 value ptb_ml_intersect_batch_bc(value *, int);
+value ptb_ml_set_light_quad(value, value);
+value ptb_ml_render_progress(value);
 
 static value boxed3(int tag, double a, double b, double c) {  /* C of float * float * float, or a float triple */
   value v = caml_alloc(3, tag);
@@ -93,6 +96,17 @@ int main(int argc, char **argv) {
   value bg = caml_alloc(2, 1);
   Field(bg, 0) = boxed3(0, 1.0, 1.0, 1.0), Field(bg, 1) = boxed3(0, 0.5, 0.7, 1.0);
   ptb_ml_set_background(scene, bg);
+
+  /* extension stubs: a light quad is accepted and removed again (NULL through the C ABI, not reachable from OCaml:
+     the scene is rebuilt instead), and the progress poll marshals a pair of ints */
+  {
+    value quad = caml_alloc(3, 0);
+    Field(quad, 0) = boxed3(0, 0.0, 1.0, -1.0), Field(quad, 1) = boxed3(0, 0.5, 0.0, 0.0), Field(quad, 2) = boxed3(0, 0.0, 0.0, 0.5);
+    ptb_ml_set_light_quad(scene, quad);
+    ptb_scene_set_light_quad(*((ptb_scene **)Data_custom_val(scene)), NULL, NULL, NULL);
+    value pr0 = ptb_ml_render_progress(Val_int(0));
+    printf("progress %ld of %ld\n", (long)Long_val(Field(pr0, 0)), (long)Long_val(Field(pr0, 1)));
+  }
 
   /* error path of the stubs: a material row that does not exist must surface as Failure, not crash */
   if (strcmp(mode, "badrow") == 0) {

@@ -121,7 +121,7 @@ def test_lit_cornell_tables():
     (lambda: lamp_over_floor(96, 64, False), 96, 64, 8, 4),
     (lambda: lamp_over_floor(96, 64, True), 96, 64, 8, 4),
     (lambda: P.cornell_box_lit(96, 96), 96, 96, 8, 16),
-    (lambda: P.cornell_box_lit(64, 64), 64, 64, 4, 1)])  # max_bounces = 1: emission must still be collected
+    (lambda: lamp_over_floor(64, 48, True), 64, 48, 4, 1)])  # max_bounces = 1: the lamp's own emission must still be collected
 def test_float64_device_mode_equals_extended_oracle(make, W, H, spp, mb):
     sc = make()
     integ = P.Integrator(sc, W, H, spp, mb)

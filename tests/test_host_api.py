@@ -190,6 +190,51 @@ def _gloo_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _gloo_band_worker(rank, world, port, q):
+    """The production exchange (distributed.render_sharded_bands): reduce-scatter by row bands, halo-row swap,
+    per-rank resolve of the own band, gather — with the oracle as the per-rank renderer and numpy as the resolve."""
+    import torch
+    import torch.distributed as dist
+    from path_tracer_ocaml_b200.distributed import alloc_padded_sums, band_rows, render_sharded_bands
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    W, H, spp, mb = 64, 37, 2, 4  # 37 rows: the last band is padded
+    scene = P.shirley_spheres(W, H)
+    osc = O.OracleScene(scene.tables())
+    w = np.zeros(9)
+    O.lib().orc_filter_binomial(5, 1, O.dptr(w))
+    sums = alloc_padded_sums(H, W, world, "cpu", dtype=torch.float64)
+    img, _ = osc.render(make_params(scene, W, H, spp, mb, rank=rank, world=world, flags=capi.PTB_FLAG_NO_FILTER))
+    sums[:H] = torch.from_numpy(img)
+
+    def resolve_rows(local):  # an image of local's height; the caller drops the two halo rows
+        return torch.from_numpy(resolve_numpy(local.numpy(), spp, w.reshape(3, 3)))
+
+    band, full = render_sharded_bands(sums, H, resolve_rows)
+    assert band.shape == (band_rows(H, world), W, 3)
+    if rank == 0:
+        whole, _ = osc.render(make_params(scene, W, H, spp, mb))
+        q.put(float(np.abs(full.numpy() - whole).max()))
+    else:
+        assert full is None
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_band_reduce_scatter_resolve_gather_over_gloo(world):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000 + world
+    procs = [ctx.Process(target=_gloo_band_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    err = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert err < 1e-12
+
+
 def test_tile_sharding_over_gloo_world_size_2():
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
