@@ -91,9 +91,15 @@ def test_device_float64_mode_matches_the_golden_png(c1_scene):
     """PTB_FLAG_F64 runs the same wavefront pipeline in float64 (own 4-wide tree, own summation order)."""
     integ = P.Integrator(c1_scene, W, H, SPP, MB, device=0)
     img = integ.render(flags=P.capi.PTB_FLAG_F64)
-    d = np.abs(quantise(img) - golden()).max(-1)
-    assert (d == 0).mean() >= 0.995, (d == 0).mean()
-    assert (d <= 1).mean() >= 0.9995, (d <= 1).mean()
+    d = np.abs(quantise(img) - golden())
+    # Knife edge: the sky's blue channel is exactly 1.0 (lerp of 1.0 and 1.0, main.ml:104-110), so an interior sky pixel
+    # is sqrt(sum of the nine filter weights) = 1 - a few 1e-16 or exactly 1, i.e. byte 254 or 255 depending on the
+    # summation order (per-sample fma splat in the reference, one 3x3 gather of per-pixel sums here).  Values within
+    # 1e-6 of a byte boundary are therefore allowed to land on either side; everything else must match exactly.
+    x = 255.0 * np.clip(img, 0.0, 1.0)
+    knife = np.abs(x - np.round(x)) < 1e-6
+    assert (d[~knife] == 0).mean() >= 0.9995, (d[~knife] == 0).mean()
+    assert d[knife].max() <= 1 and d.max() <= 2
 
 
 @pytest.mark.gpu
