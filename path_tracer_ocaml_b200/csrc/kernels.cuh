@@ -178,18 +178,26 @@ __device__ __forceinline__ Quat<R> frame_from_normal(V3<R> n) {
 // float: straight-line.  A negative discriminant makes sqrt.approx return NaN, NaN propagates into t and
 // every comparison with NaN is false, so the miss needs no branch (the Rust kernel's NaN masking,
 // lib.rs:160-166, is the same idea).
-__device__ __forceinline__ void sphere_test(Vec4<float> s, V3<float> o, V3<float> d, float a, float inv_a,
-                                            float tmin, float &tbest, int &best, int id) {
+// UNIT: the ray direction has unit length (every ray of the render pipeline: Camera.ray normalizes, world_ray rotates
+// unit vectors), so a = d.d = 1 drops out: three multiplies and two live registers less per test.
+template <bool UNIT>
+__device__ __forceinline__ bool sphere_test_f(Vec4<float> s, V3<float> o, V3<float> d, float a, float inv_a,
+                                              float tmin, float &tbest) {
   const V3<float> f = {s.x - o.x, s.y - o.y, s.z - o.z};
   const float bp = dot(f, d);
-  const float boa = bp * inv_a;
+  const float boa = UNIT ? bp : bp * inv_a;
   const V3<float> w = {fmaf(d.x, boa, -f.x), fmaf(d.y, boa, -f.y), fmaf(d.z, boa, -f.z)};
   const float disc = fmaf(-w.x, w.x, fmaf(-w.y, w.y, fmaf(-w.z, w.z, s.w)));
-  const float q = bp + copysignf(r_sqrt_fast(a * disc), bp);
+  const float q = bp + copysignf(r_sqrt_fast(UNIT ? disc : a * disc), bp);
   const float c = fmaf(f.x, f.x, fmaf(f.y, f.y, fmaf(f.z, f.z, -s.w)));
-  const float t = (c > 0.0f) ? c * r_rcp(q) : q * inv_a;
+  const float t = (c > 0.0f) ? c * r_rcp(q) : (UNIT ? q : q * inv_a);
   const bool ok = (t >= tmin) && (t <= tbest);  // `<=`: a later equal t wins (lib.rs:171-176)
   tbest = ok ? t : tbest;
+  return ok;
+}
+__device__ __forceinline__ void sphere_test(Vec4<float> s, V3<float> o, V3<float> d, float a, float inv_a,
+                                            float tmin, float &tbest, int &best, int id) {
+  const bool ok = sphere_test_f<false>(s, o, d, a, inv_a, tmin, tbest);
   best = ok ? id : best;
 }
 template <class R>
@@ -392,13 +400,14 @@ struct SceneRef {
     if (SMEM) return lds_u8(s_kinds + (unsigned)idx);
     return (int)__ldg(g_kinds + idx);
   }
-  // row at byte offset `off` of node `node`
+  // row at byte offset `off` of node `node`.  SMEM: `node` IS the node's shared-window address — the block rewrites
+  // the inner-node references of the staged tree once, so a node visit starts without an address multiply
   __device__ __forceinline__ Vec4<R> nrow(int node, unsigned off) const {
-    if (SMEM) return lds_vec4(s_nodes + (unsigned)node * (unsigned)sizeof(Node4<R>) + off, R());
+    if (SMEM) return lds_vec4((unsigned)node + off, R());
     return ldg_vec4(reinterpret_cast<const Vec4<R> *>(g_nodes + (size_t)node * sizeof(Node4<R>) + off));
   }
   __device__ __forceinline__ int4 children(int node) const {
-    if (SMEM) return lds_int4(s_nodes + (unsigned)node * (unsigned)sizeof(Node4<R>) + 6u * ROW);
+    if (SMEM) return lds_int4((unsigned)node + 6u * ROW);
     return __ldg(reinterpret_cast<const int4 *>(g_nodes + (size_t)node * sizeof(Node4<R>) + 6 * ROW));
   }
   // (cx, cy, cz, r^2): the shared-memory copy is squared once when the block stages it
@@ -451,8 +460,10 @@ struct Lane {
   f32x2_t ix2, iy2, iz2, nox2, noy2, noz2;
 };
 
-template <class R>
-__device__ __forceinline__ void lane_init(Lane<R> &L, V3<R> o, V3<R> d, R tmin, R tmax, unsigned sp0) {
+// UNIT: unit-length direction, a = 1 is not stored (float render pipeline).  root: the root's `cur` value (node
+// index 0, or its shared-memory address when the staged tree holds addresses)
+template <class R, bool UNIT = false>
+__device__ __forceinline__ void lane_init(Lane<R> &L, V3<R> o, V3<R> d, R tmin, R tmax, unsigned sp0, int root = 0) {
   constexpr unsigned ROW = 4u * (unsigned)sizeof(R);
   auto safe_rcp = [](R x) {
     return (r_abs(x) < Lim<R>::tiny()) ? r_copysign(R(1) / Lim<R>::tiny(), x) : r_rcp(x);
@@ -464,10 +475,12 @@ __device__ __forceinline__ void lane_init(Lane<R> &L, V3<R> o, V3<R> d, R tmin, 
     L.ix2 = pack2(L.idir.x, L.idir.x), L.iy2 = pack2(L.idir.y, L.idir.y), L.iz2 = pack2(L.idir.z, L.idir.z);
     L.nox2 = pack2(-L.oid.x, -L.oid.x), L.noy2 = pack2(-L.oid.y, -L.oid.y), L.noz2 = pack2(-L.oid.z, -L.oid.z);
   }
-  L.a = dot(d, d);
-  L.inv_a = r_rcp(L.a);
+  if constexpr (!UNIT) {
+    L.a = dot(d, d);
+    L.inv_a = r_rcp(L.a);
+  }
   L.tmin = tmin, L.tbest = tmax;
-  L.best = -1, L.cur = 0;
+  L.best = -1, L.cur = root;
   L.sp = sp0;
   L.onx = d.x >= R(0) ? 0u : 3u * ROW;  // rows: lo.x lo.y lo.z hi.x hi.y hi.z
   L.ony = d.y >= R(0) ? ROW : 4u * ROW;
@@ -559,15 +572,29 @@ __device__ __forceinline__ void node_phase(Lane<R> &L, const SceneRef<R, SMEM> &
   }
 }
 
-template <class R, bool SMEM, bool TMIN0>
+template <class R, bool SMEM, bool TMIN0, bool UNIT>
 __device__ __forceinline__ void leaf_phase(Lane<R> &L, const SceneRef<R, SMEM> &S) {
   const unsigned code = ~(unsigned)L.cur;
   const int first = (int)(code & 0x3FFFFFFu);
   const int cnt = (int)((code >> 26) & 15u) + 1;
   const R tmin = TMIN0 ? R(0) : L.tmin;
   if (((code >> 30) & 1u) == 0u) {
+    if constexpr (SMEM && sizeof(R) == 4) {
+      // walk the leaf's records by shared-memory address; the hit is remembered as an address and turned into a
+      // slot once per leaf (3 instructions of loop control per sphere instead of 6)
+      unsigned addr = S.s_spheres + (unsigned)first * 16u, hit = 0u;
+      const unsigned end = addr + (unsigned)cnt * 16u;
 #pragma unroll 1
-    for (int i = 0; i < cnt; ++i) sphere_test(S.sphere(first + i), L.o, L.d, L.a, L.inv_a, tmin, L.tbest, L.best, first + i);
+      do {
+        const bool ok = sphere_test_f<UNIT>(lds_vec4(addr, float()), L.o, L.d, UNIT ? 1.0f : L.a, UNIT ? 1.0f : L.inv_a, tmin, L.tbest);
+        hit = ok ? addr : hit;
+        addr += 16u;
+      } while (addr < end);
+      if (hit) L.best = (int)((hit - S.s_spheres) >> 4);
+    } else {
+#pragma unroll 1
+      for (int i = 0; i < cnt; ++i) sphere_test(S.sphere(first + i), L.o, L.d, L.a, L.inv_a, tmin, L.tbest, L.best, first + i);
+    }
   } else {
 #pragma unroll 1
     for (int i = 0; i < cnt; ++i)
@@ -733,7 +760,7 @@ constexpr int LEAF_MIN = 8;  // lanes holding a leaf before the warp runs the le
 constexpr unsigned WS_NEXT = 0, WS_END = 1, WS_FETCHED = 2, WS_SEG = 3 /* base,fill x 3 kinds */, WS_STAGED = 9,
                    WS_REM_BASE = 10, WS_REM_CNT = 11 /* whole segments claimed but not opened yet */,
                    WS_SEEN = 12 /* the cursor at the last claim */, WS_IB = 13, WS_QB = 14 /* GEN: pixel-list index and
-                   pass of entry WS_NEXT */, WS_WORDS = 16;
+                   pass of entry WS_NEXT */, WS_KINDS = 15 /* shared-window address of the material-kind table */, WS_WORDS = 16;
 constexpr unsigned RING = 32;  // entries of the per-warp staging ring for incoming rays
 
 // dynamic shared memory per thread besides the staged scene: stack + payload slot + share of the warp record
@@ -745,7 +772,9 @@ __host__ __device__ constexpr size_t trace_smem_per_thread(int stack_cap, bool s
 
 // GEN: bounce 0 — the rays are the camera samples [0, gen_n) of the batch, generated in registers
 // (camera_sample) instead of being read from `rays`.
-template <class R, int MODE, bool SMEM, bool GEN>
+// BLK: the block size when it is known at compile time (the 1024-thread float launch of shared-memory scenes: the
+// stack's level stride becomes an immediate), 0 = blockDim.x.
+template <class R, int MODE, bool SMEM, bool GEN, int BLK = 0>
 __global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, SMEM ? 1 : (sizeof(R) == 8 ? 1 : 3))
     k_trace(DScene<R> sc, GenConst gen, unsigned gen_n, Queue<R> rays, const unsigned *__restrict__ nseg_ptr, unsigned nseg_imm,
             unsigned *__restrict__ cursor, int refill_below, Queue<R> q0, unsigned q_slots,
@@ -754,10 +783,11 @@ __global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, SM
   extern __shared__ __align__(16) unsigned char smem[];
   const unsigned nseg = nseg_ptr ? *nseg_ptr : nseg_imm;  // segments in the input ray queue
   const int tid = threadIdx.x;
+  const unsigned nthreads = BLK ? (unsigned)BLK : blockDim.x;
   const unsigned lane = tid & 31;
   // claim granularity: a quarter, half or whole segment, so that a small launch (late bounces) still
   // spreads over every persistent warp and a big one pays one cursor atomic per 128 rays
-  const unsigned per_warp = nseg * (unsigned)SEG / (gridDim.x * (blockDim.x >> 5));
+  const unsigned per_warp = nseg * (unsigned)SEG / (gridDim.x * (nthreads >> 5));
   const unsigned claim_shift = per_warp >= 512u ? 0u : (per_warp >= 256u ? 1u : 2u);  // units per segment = 1 << shift
   const unsigned smem_base = (unsigned)__cvta_generic_to_shared(smem);
   SceneRef<R, SMEM> S;
@@ -775,10 +805,10 @@ __global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, SM
     const int4 *s1 = reinterpret_cast<const int4 *>(sc.spheres);
     const int4 *s2 = reinterpret_cast<const int4 *>(sc.tris);
     const int4 *s3 = reinterpret_cast<const int4 *>(sc.prim_kind);
-    for (unsigned i = tid; i < nb / 16; i += blockDim.x) dst[i] = s0[i];
-    for (unsigned i = tid; i < sb / 16; i += blockDim.x) dst[nb / 16 + i] = s1[i];
-    for (unsigned i = tid; i < tb / 16; i += blockDim.x) dst[(nb + sb) / 16 + i] = s2[i];
-    for (unsigned i = tid; i < kb / 16; i += blockDim.x) dst[(nb + sb + tb) / 16 + i] = s3[i];
+    for (unsigned i = tid; i < nb / 16; i += nthreads) dst[i] = s0[i];
+    for (unsigned i = tid; i < sb / 16; i += nthreads) dst[nb / 16 + i] = s1[i];
+    for (unsigned i = tid; i < tb / 16; i += nthreads) dst[(nb + sb) / 16 + i] = s2[i];
+    for (unsigned i = tid; i < kb / 16; i += nthreads) dst[(nb + sb + tb) / 16 + i] = s3[i];
     S.s_nodes = smem_base, S.s_spheres = smem_base + nb, S.s_tris = smem_base + nb + sb;
     S.s_kinds = smem_base + nb + sb + tb;
     __syncthreads();
@@ -787,7 +817,13 @@ __global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, SM
     asm volatile("" : "+r"(S.s_nodes), "+r"(S.s_spheres));
     // the shared-memory sphere records carry r^2 (what the intersection test needs)
     Vec4<R> *ssph = reinterpret_cast<Vec4<R> *>(smem + nb);
-    for (unsigned i = tid; i < (unsigned)sc.n_spheres; i += blockDim.x) ssph[i].w *= ssph[i].w;
+    for (unsigned i = tid; i < (unsigned)sc.n_spheres; i += nthreads) ssph[i].w *= ssph[i].w;
+    // ... and the staged tree refers to inner nodes by their shared-window ADDRESS (SceneRef::nrow)
+    Node4<R> *snodes = reinterpret_cast<Node4<R> *>(smem);
+    for (unsigned i = tid; i < 4u * (unsigned)sc.n_nodes; i += nthreads) {
+      const int c = snodes[i >> 2].child[i & 3u];
+      if (c >= 0) snodes[i >> 2].child[i & 3u] = (int)(smem_base + (unsigned)c * (unsigned)sizeof(Node4<R>));
+    }
     __syncthreads();
   }
   // traversal stack: stack[level][thread], entry = (ref, t_near); level 0 is the sentinel
@@ -795,14 +831,14 @@ __global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, SM
   Stack<R, !SMEM> K;
   unsigned sp0, sp_limit, pay_base;
   if constexpr (SMEM) {
-    K.stride = blockDim.x * ENTRY;
+    K.stride = nthreads * ENTRY;
     const unsigned stk0 = smem_base + scene_bytes + (unsigned)tid * ENTRY;
     K.store(stk0, TRAV_DONE, -Lim<R>::inf());
     sp0 = stk0 + K.stride;
     sp_limit = stk0 + (unsigned)sc.stack_cap * K.stride;  // entries [1, stack_cap) hold pushes
     pay_base = smem_base + scene_bytes + (unsigned)sc.stack_cap * K.stride;
   } else {
-    K.s_stride = blockDim.x * ENTRY;
+    K.s_stride = nthreads * ENTRY;
     K.s_base = smem_base + (unsigned)tid * ENTRY;
     K.store(0u, TRAV_DONE, -Lim<R>::inf());
     sp0 = 1u;
@@ -811,14 +847,17 @@ __global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, SM
   }
   // per-thread payload slot and per-warp record
   const unsigned pay_v = pay_base + (unsigned)tid * (unsigned)sizeof(Vec4<R>);
-  const unsigned pay_r = pay_base + blockDim.x * (unsigned)sizeof(Vec4<R>) + (unsigned)tid * (unsigned)sizeof(R);
-  const unsigned ws = pay_base + blockDim.x * (unsigned)(sizeof(Vec4<R>) + sizeof(R)) + ((unsigned)tid >> 5) * (WS_WORDS * 4u);
+  const unsigned pay_r = pay_base + nthreads * (unsigned)sizeof(Vec4<R>) + (unsigned)tid * (unsigned)sizeof(R);
+  const unsigned ws = pay_base + nthreads * (unsigned)(sizeof(Vec4<R>) + sizeof(R)) + ((unsigned)tid >> 5) * (WS_WORDS * 4u);
   if (lane < WS_WORDS)
     sts_i32(ws + lane * 4u, (lane >= WS_SEG && lane < WS_STAGED && ((lane - WS_SEG) & 1u) == 0u) ? (int)NO_SEG : 0);
+  if (SMEM && lane == WS_KINDS) sts_i32(ws + WS_KINDS * 4u, (int)S.s_kinds);  // read back at every flush (one LDS)
   __syncwarp();
+  constexpr bool UNIT = MODE == 0 && sizeof(R) == 4;  // render pipeline, float: unit directions (sphere_test_f)
+  const int root = SMEM ? (int)smem_base : 0;
   constexpr unsigned VB = (unsigned)sizeof(Vec4<R>);
   // staging ring of this warp: RING origins, then RING directions (entry i of the queue sits in slot i % RING)
-  const unsigned ring_a = pay_base + blockDim.x * (unsigned)(sizeof(Vec4<R>) + sizeof(R)) + (blockDim.x >> 5) * (WS_WORDS * 4u) +
+  const unsigned ring_a = pay_base + nthreads * (unsigned)(sizeof(Vec4<R>) + sizeof(R)) + (nthreads >> 5) * (WS_WORDS * 4u) +
                           ((unsigned)tid >> 5) * (2u * RING * VB);
   const unsigned ring_b = ring_a + RING * VB;
 
@@ -854,7 +893,10 @@ __global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, SM
             atomicAdd(&sums[3 * (size_t)pixel + 1], pv.y * bg.y);
             atomicAdd(&sums[3 * (size_t)pixel + 2], pv.z * bg.z);
           } else if (enqueue_hits) {
-            kind = S.kind(L.best, sc.n_spheres);
+            if (SMEM)
+              kind = lds_u8((unsigned)lds_i32(ws + WS_KINDS * 4u) + (unsigned)((L.best & 0x3FFFFFFF) + (((L.best >> 30) & 1) ? sc.n_spheres : 0)));
+            else
+              kind = S.kind(L.best, sc.n_spheres);
           }
         }
         // per-material segmented queues: no global atomic unless a segment fills up.  Lane k (k < 3) keeps the
@@ -930,7 +972,7 @@ __global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, SM
               const Vec4<R> pv = {R(1), R(1), R(1), i2r(pixel, R())};
               sts_vec4(pay_v, pv);
               sts_r(pay_r, i2r(offset, R()));
-              lane_init<R>(L, V3<R>{R(0), R(0), R(0)}, dir, R(0), Lim<R>::tmax(), sp0);
+              lane_init<R, UNIT>(L, V3<R>{R(0), R(0), R(0)}, dir, R(0), Lim<R>::tmax(), sp0, root);
             } else {
               const Vec4<R> A = lds_vec4(ring_a + (ray_i % RING) * VB, R()), B = lds_vec4(ring_b + (ray_i % RING) * VB, R());
               if (MODE == 0) {
@@ -938,9 +980,11 @@ __global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, SM
                 cp_async_vec4<R>(pay_v, rays.C + ray_i);
                 sts_r(pay_r, B.w);
               }
-              lane_init<R>(L, V3<R>{A.x, A.y, A.z}, V3<R>{B.x, B.y, B.z}, (MODE == 0) ? R(0) : tmin_arg,
-                           (MODE == 0) ? Lim<R>::tmax() : tmax_arg, sp0);
+              lane_init<R, UNIT>(L, V3<R>{A.x, A.y, A.z}, V3<R>{B.x, B.y, B.z}, (MODE == 0) ? R(0) : tmin_arg,
+                                 (MODE == 0) ? Lim<R>::tmax() : tmax_arg, sp0, root);
             }
+            // (Visiting the root right here, for all refilled lanes at once — broadcast shared-memory reads, no loop
+            // iteration — was measured: +4.7 % trace time, profiles/README.md round 2.)
           }
           idle_left &= ~__ballot_sync(0xffffffffu, mine);  // (also orders the ring reads before the next copies into it)
           next += take;
@@ -956,7 +1000,7 @@ __global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, SM
             const unsigned nunits = nseg << claim_shift;
             unsigned g = 1u;
             if (claim_shift == 0u) {
-              const unsigned seen = (unsigned)lds_i32(ws + WS_SEEN * 4u), nwarps = gridDim.x * (blockDim.x >> 5);
+              const unsigned seen = (unsigned)lds_i32(ws + WS_SEEN * 4u), nwarps = gridDim.x * (nthreads >> 5);
               const unsigned left = seen < nunits ? nunits - seen : 0u;
               g = left > 16u * nwarps ? 4u : (left > 8u * nwarps ? 2u : 1u);
             }
@@ -1052,7 +1096,7 @@ __global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, SM
       const bool at_leaf = (unsigned)(L.cur - (TRAV_POP + 1)) < (unsigned)(0 - (TRAV_POP + 1));  // TRAV_POP < cur < 0
       const unsigned lm = __ballot_sync(0xffffffffu, at_leaf);
       if (__popc(lm) >= LEAF_MIN || lm == act) {  // (lm == 0 never equals act inside the loop)
-        if (at_leaf) leaf_phase<R, SMEM, MODE == 0>(L, S);
+        if (at_leaf) leaf_phase<R, SMEM, MODE == 0, UNIT>(L, S);
       }
       if (L.cur == TRAV_POP) pop_phase<R, !SMEM>(L, K);
       act = __ballot_sync(0xffffffffu, L.cur > TRAV_DONE);

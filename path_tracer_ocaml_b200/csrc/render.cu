@@ -395,6 +395,11 @@ static int trace_config(DeviceState *d, const DScene<R> &sc, size_t scene_bytes,
     CK(cudaFuncSetAttribute(k_trace<R, MODE, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl->smem));
     if (MODE == 0)
       CK(cudaFuncSetAttribute(k_trace<R, MODE, true, MODE == 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl->smem));
+    if (sizeof(R) == 4 && tl->block == 1024) {  // the block size is a compile-time constant in this instantiation
+      CK(cudaFuncSetAttribute(k_trace<R, MODE, true, false, sizeof(R) == 4 ? 1024 : 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl->smem));
+      if (MODE == 0)
+        CK(cudaFuncSetAttribute(k_trace<R, MODE, true, MODE == 0, sizeof(R) == 4 ? 1024 : 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl->smem));
+    }
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<R, MODE, true, false>, tl->block, tl->smem));
     if (per_sm < 1) return fail(PTB_E_CUDA, "trace: kernel cannot be resident");
@@ -430,20 +435,26 @@ static void launch_trace(const TraceLaunch &tl, cudaStream_t st, const DScene<R>
   GenConst g;
   std::memset(&g, 0, sizeof g);
   if (gen) g = *gen;
-#define PTB_LAUNCH(SM, GN)                                                                                             \
-  k_trace<R, MODE, SM, GN><<<tl.grid, tl.block, tl.smem, st>>>(sc, g, gen_n, rays, nseg_ptr, nseg_imm, cursor,        \
-                                                               refill_below(), mq, mq_slots, nseg_mat,                    \
-                                                               n_traced, enqueue_hits, sums, tmin, tmax, out_t, out_prim)
+#define PTB_LAUNCH(SM, GN, BK)                                                                                         \
+  k_trace<R, MODE, SM, GN, BK><<<tl.grid, tl.block, tl.smem, st>>>(sc, g, gen_n, rays, nseg_ptr, nseg_imm, cursor,    \
+                                                                   refill_below(), mq, mq_slots, nseg_mat,                \
+                                                                   n_traced, enqueue_hits, sums, tmin, tmax, out_t, out_prim)
+  constexpr int FIXED = sizeof(R) == 4 ? 1024 : 0;  // float, shared-memory scene, full block: compile-time block size
+  const bool fixed = FIXED != 0 && tl.scene_smem && tl.block == 1024;
   if (MODE == 0 && gen) {
-    if (tl.scene_smem)
-      PTB_LAUNCH(true, MODE == 0);
+    if (fixed)
+      PTB_LAUNCH(true, MODE == 0, FIXED);
+    else if (tl.scene_smem)
+      PTB_LAUNCH(true, MODE == 0, 0);
     else
-      PTB_LAUNCH(false, MODE == 0);
+      PTB_LAUNCH(false, MODE == 0, 0);
   } else {
-    if (tl.scene_smem)
-      PTB_LAUNCH(true, false);
+    if (fixed)
+      PTB_LAUNCH(true, false, FIXED);
+    else if (tl.scene_smem)
+      PTB_LAUNCH(true, false, 0);
     else
-      PTB_LAUNCH(false, false);
+      PTB_LAUNCH(false, false, 0);
   }
 #undef PTB_LAUNCH
 }
