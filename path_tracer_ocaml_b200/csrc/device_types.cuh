@@ -66,7 +66,7 @@ struct DScene {
   int32_t scene_in_smem;  // 1: nodes+spheres+tris are staged in shared memory by every block
   int32_t stack_cap;      // traversal stack entries per thread
   int32_t bg_kind;
-  R bg0[3], bg1[3];
+  R bg0[3], bg1[3], bgd[3];  // bgd = bg1 - bg0
   // extension (ptb_scene_set_light_quad / PTB_MAT_EMISSIVE): diffuse_plus_light = Mix (Diffuse, Quad_light)
   int32_t has_light, has_emissive;
   R light_o[3], light_u[3], light_v[3];
@@ -80,11 +80,21 @@ struct DScene {
 // counter once per SEG entries (instead of one contended return-value atomic per warp flush); a
 // consumer claims whole segments.  Only the last segment a warp opened can be partially filled.
 constexpr int SEG = 128;
+// Memory layout: SEGMENT-INTERLEAVED.  One allocation; segment s occupies 3 * SEG consecutive Vec4 as
+// [A x SEG][B x SEG][C x SEG].  A warp that works through a segment therefore touches ONE region of memory (one open
+// DRAM page stream in, one out, instead of three each), the three fields of an entry are at constant distances
+// (one address computation + immediates), and 32 consecutive entries of a field are 512 contiguous bytes — the unit
+// k_shade moves with bulk copies (cp.async.bulk).
 template <class R>
 struct Queue {
-  Vec4<R> *A, *B, *C;
+  Vec4<R> *base;
   int32_t *seg_count;
+  static __host__ __device__ __forceinline__ unsigned idx(unsigned e) { return e + ((e >> 7) << 8); }  // e/SEG*3*SEG + e%SEG
+  __host__ __device__ __forceinline__ Vec4<R> *A(unsigned e) const { return base + idx(e); }
+  __host__ __device__ __forceinline__ Vec4<R> *B(unsigned e) const { return base + idx(e) + SEG; }
+  __host__ __device__ __forceinline__ Vec4<R> *C(unsigned e) const { return base + idx(e) + 2 * SEG; }
 };
+static_assert(SEG == 128, "Queue::idx hard-codes SEG = 128");
 
 struct Ctl {
   unsigned int nseg_rays[MAX_BOUNCES + 1];         // segments of the ray queue entering bounce b

@@ -324,10 +324,15 @@ __device__ __forceinline__ void cp_async_scalar(unsigned saddr, const float *g) 
 __device__ __forceinline__ void cp_async_scalar(unsigned saddr, const double *g) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(saddr), "l"(g) : "memory");
 }
-template <class R>
+template <int OFF>
+__device__ __forceinline__ void cp_async16_off(unsigned saddr, const void *g) {  // [g + OFF]: the offset is an immediate
+  asm volatile("cp.async.cg.shared.global [%0], [%1+%2], 16;" ::"r"(saddr), "l"(g), "n"(OFF) : "memory");
+}
+// FIELD: which of the three fields of a segment-interleaved queue entry (0 = A, 1 = B, 2 = C), `g` = the entry's A
+template <class R, int FIELD = 0>
 __device__ __forceinline__ void cp_async_vec4(unsigned saddr, const Vec4<R> *g) {
-#pragma unroll
-  for (unsigned k = 0; k < sizeof(Vec4<R>) / 16; ++k) cp_async16(saddr + 16u * k, reinterpret_cast<const char *>(g) + 16 * k);
+  cp_async16_off<FIELD * SEG * (int)sizeof(Vec4<R>)>(saddr, g);
+  if constexpr (sizeof(Vec4<R>) == 32) cp_async16_off<FIELD * SEG * (int)sizeof(Vec4<R>) + 16>(saddr + 16u, g);
 }
 // traversal-stack entry = (child ref, t_near): 8 B in float (one 64-bit shared access), 16 B in double
 __device__ __forceinline__ void stk_store(unsigned addr, int ref, float t) {
@@ -635,6 +640,8 @@ __device__ __forceinline__ V3<R> background(const DScene<R> &sc, V3<R> d) {
   // skips the reference's re-normalisation; float64 keeps it)
   V3<R> dn = sizeof(R) == 4 ? d : normalize(d);
   R t = R(0.5) * (dn.y + R(1));
+  if constexpr (sizeof(R) == 4)  // c0 + t (c1 - c0): one FFMA per channel (float rounding only; float64 keeps lerp's form)
+    return {r_fma(t, sc.bgd[0], sc.bg0[0]), r_fma(t, sc.bgd[1], sc.bg0[1]), r_fma(t, sc.bgd[2], sc.bg0[2])};
   R s = R(1) - t;
   return {sc.bg0[0] * s + sc.bg1[0] * t, sc.bg0[1] * s + sc.bg1[1] * t, sc.bg0[2] * s + sc.bg1[2] * t};
 }
@@ -644,6 +651,14 @@ __device__ __forceinline__ V3<R> background(const DScene<R> &sc, V3<R> d) {
 // seg_base/seg_fill are warp-uniform: the warp's open segment in this queue (seg_base = NO_SEG: none).
 // ---------------------------------------------------------------------------------------------
 constexpr unsigned NO_SEG = 0xffffffffu;
+// A producer warp takes segments from the queue's global counter SEG_GROUP at a time (one return-value atomic per
+// SEG_GROUP * SEG entries) and fills them one after the other; the ones it never opens are closed with count 0 when
+// the warp retires (consumers skip empty segments).  An open segment whose index is not the last of its group has
+// its successor for free.
+constexpr unsigned SEG_GROUP = 4;
+__device__ __forceinline__ bool seg_has_next(unsigned seg_base) {
+  return seg_base != NO_SEG && ((seg_base / (unsigned)SEG) & (SEG_GROUP - 1u)) != SEG_GROUP - 1u;
+}
 __device__ __forceinline__ unsigned seg_append(bool want, unsigned &seg_base, unsigned &seg_fill,
                                                unsigned *__restrict__ nseg, int32_t *__restrict__ seg_count,
                                                unsigned lane, unsigned lt_mask) {
@@ -656,20 +671,29 @@ __device__ __forceinline__ unsigned seg_append(bool want, unsigned &seg_base, un
     seg_fill += cnt;
     return dst;
   }
-  unsigned s = 0;
-  if (lane == 0) {
-    s = atomicAdd(nseg, 1u);
-    if (seg_base != NO_SEG) seg_count[seg_base / SEG] = SEG;  // the old segment is (or becomes) full
+  unsigned nb;
+  if (seg_has_next(seg_base)) {  // warp-uniform
+    nb = seg_base + (unsigned)SEG;
+    if (lane == 0) seg_count[seg_base / SEG] = SEG;
+  } else {
+    unsigned s = 0;
+    if (lane == 0) {
+      s = atomicAdd(nseg, SEG_GROUP);
+      if (seg_base != NO_SEG) seg_count[seg_base / SEG] = SEG;  // the old segment is (or becomes) full
+    }
+    nb = __shfl_sync(0xffffffffu, s, 0) * (unsigned)SEG;
   }
-  s = __shfl_sync(0xffffffffu, s, 0);
-  const unsigned dst = rank < room ? seg_base + seg_fill + rank : s * SEG + (rank - room);
-  seg_base = s * SEG;
+  const unsigned dst = rank < room ? seg_base + seg_fill + rank : nb + (rank - room);
+  seg_base = nb;
   seg_fill = cnt - room;
   return dst;
 }
+// the warp retires: its open segment gets its fill count, the unopened rest of the group is empty
 __device__ __forceinline__ void seg_close(unsigned seg_base, unsigned seg_fill, int32_t *__restrict__ seg_count,
                                           unsigned lane) {
-  if (seg_base != NO_SEG && lane == 0) seg_count[seg_base / SEG] = (int32_t)seg_fill;
+  if (seg_base == NO_SEG) return;
+  const unsigned s = seg_base / (unsigned)SEG, last = s | (SEG_GROUP - 1u);
+  if (s + lane <= last) seg_count[s + lane] = lane == 0 ? (int32_t)seg_fill : 0;
 }
 
 // =================================================================================================
@@ -728,9 +752,10 @@ __global__ void __launch_bounds__(256) k_raygen(GenConst g, unsigned n, Queue<R>
     if (dbg_cx) dbg_cx[k] = cx;
     if (dbg_cy) dbg_cy[k] = cy;
     V3<R> dir = normalize(V3<R>{R(ddx), R(ddy), R(-1)});
-    out.A[k] = {R(0), R(0), R(0), R(0)};
-    out.B[k] = {dir.x, dir.y, dir.z, i2r(offset, R())};
-    out.C[k] = {R(1), R(1), R(1), i2r(pixel, R())};
+    Vec4<R> *e = out.A(k);
+    e[0] = {R(0), R(0), R(0), R(0)};
+    e[SEG] = {dir.x, dir.y, dir.z, i2r(offset, R())};
+    e[2 * SEG] = {R(1), R(1), R(1), i2r(pixel, R())};
     if (k % SEG == 0) out.seg_count[k / SEG] = (int32_t)(n - k < (unsigned)SEG ? n - k : (unsigned)SEG);  // dense
   }
 }
@@ -750,7 +775,7 @@ __global__ void __launch_bounds__(256) k_raygen(GenConst g, unsigned n, Queue<R>
 // per-thread slot at refill and read back at flush, and the warp-uniform bookkeeping (claimed input
 // range, open output segments, statistics) sits in a per-warp record.
 //
-// Dynamic shared memory: [scene (SMEM)] [stack: stack_cap x threads x ENTRY] [payload: threads x (Vec4 + R)]
+// Dynamic shared memory: [scene (SMEM)] [stack: stack_cap x threads x ENTRY] [payload: threads x (Vec4 + R + int)]
 //                        [warp records: warps x WS_WORDS x 4 B] [staging rings: warps x RING x 2 Vec4]
 //
 // Incoming rays never wait on HBM/L2: each warp keeps the next RING entries (origin, direction) of its claimed
@@ -760,13 +785,14 @@ constexpr int LEAF_MIN = 8;  // lanes holding a leaf before the warp runs the le
 constexpr unsigned WS_NEXT = 0, WS_END = 1, WS_FETCHED = 2, WS_SEG = 3 /* base,fill x 3 kinds */, WS_STAGED = 9,
                    WS_REM_BASE = 10, WS_REM_CNT = 11 /* whole segments claimed but not opened yet */,
                    WS_SEEN = 12 /* the cursor at the last claim */, WS_IB = 13, WS_QB = 14 /* GEN: pixel-list index and
-                   pass of entry WS_NEXT */, WS_KINDS = 15 /* shared-window address of the material-kind table */, WS_WORDS = 16;
+                   pass of entry WS_NEXT */, WS_KINDS = 15 /* shared-window address of the material-kind table */,
+                   WS_ROOT = 16 /* `cur` of the root node */, WS_WORDS = 20;
 constexpr unsigned RING = 32;  // entries of the per-warp staging ring for incoming rays
 
 // dynamic shared memory per thread besides the staged scene: stack + payload slot + share of the warp record
 template <class R>
 __host__ __device__ constexpr size_t trace_smem_per_thread(int stack_cap, bool stack_in_smem) {
-  return (size_t)(stack_in_smem ? stack_cap : PTB_STACK_HOT) * 2u * sizeof(R) + sizeof(Vec4<R>) + sizeof(R) +
+  return (size_t)(stack_in_smem ? stack_cap : PTB_STACK_HOT) * 2u * sizeof(R) + sizeof(Vec4<R>) + sizeof(R) + 4u /* sp0 */ +
          (WS_WORDS * 4u + 31u) / 32u + RING * 2u * sizeof(Vec4<R>) / 32u;
 }
 
@@ -848,16 +874,22 @@ __global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, SM
   // per-thread payload slot and per-warp record
   const unsigned pay_v = pay_base + (unsigned)tid * (unsigned)sizeof(Vec4<R>);
   const unsigned pay_r = pay_base + nthreads * (unsigned)sizeof(Vec4<R>) + (unsigned)tid * (unsigned)sizeof(R);
-  const unsigned ws = pay_base + nthreads * (unsigned)(sizeof(Vec4<R>) + sizeof(R)) + ((unsigned)tid >> 5) * (WS_WORDS * 4u);
+  // this thread's first free stack entry, kept in shared memory: a refill reads it back with one LDS instead of
+  // re-deriving it from the thread index and the scene size (registers are too scarce to hold it across the loop)
+  // (float: the same 4-byte stride as the pay_r array right before it, so the slot is pay_r + a constant)
+  const unsigned sp0_slot = sizeof(R) == 4 ? pay_r + nthreads * 4u
+                                           : pay_base + nthreads * (unsigned)(sizeof(Vec4<R>) + sizeof(R)) + (unsigned)tid * 4u;
+  sts_i32(sp0_slot, (int)sp0);
+  const unsigned ws = pay_base + nthreads * (unsigned)(sizeof(Vec4<R>) + sizeof(R) + 4u) + ((unsigned)tid >> 5) * (WS_WORDS * 4u);
   if (lane < WS_WORDS)
     sts_i32(ws + lane * 4u, (lane >= WS_SEG && lane < WS_STAGED && ((lane - WS_SEG) & 1u) == 0u) ? (int)NO_SEG : 0);
   if (SMEM && lane == WS_KINDS) sts_i32(ws + WS_KINDS * 4u, (int)S.s_kinds);  // read back at every flush (one LDS)
+  if (lane == WS_ROOT) sts_i32(ws + WS_ROOT * 4u, SMEM ? (int)smem_base : 0);     // read back at every refill
   __syncwarp();
   constexpr bool UNIT = MODE == 0 && sizeof(R) == 4;  // render pipeline, float: unit directions (sphere_test_f)
-  const int root = SMEM ? (int)smem_base : 0;
   constexpr unsigned VB = (unsigned)sizeof(Vec4<R>);
   // staging ring of this warp: RING origins, then RING directions (entry i of the queue sits in slot i % RING)
-  const unsigned ring_a = pay_base + nthreads * (unsigned)(sizeof(Vec4<R>) + sizeof(R)) + (nthreads >> 5) * (WS_WORDS * 4u) +
+  const unsigned ring_a = pay_base + nthreads * (unsigned)(sizeof(Vec4<R>) + sizeof(R) + 4u) + (nthreads >> 5) * (WS_WORDS * 4u) +
                           ((unsigned)tid >> 5) * (2u * RING * VB);
   const unsigned ring_b = ring_a + RING * VB;
 
@@ -899,41 +931,45 @@ __global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, SM
               kind = S.kind(L.best, sc.n_spheres);
           }
         }
-        // per-material segmented queues: no global atomic unless a segment fills up.  Lane k (k < 3) keeps the
-        // books of material kind k (its open segment in the warp record); every lane then fetches the numbers
-        // of ITS kind with three shuffles.
+        // Per-material segmented queues: no global atomic unless a segment fills up.  Every hit lane reads the open
+        // segment (base, fill) of ITS kind from the warp record (lanes of one kind read the same word: a broadcast),
+        // ranks itself among the lanes of that kind, and the kind's first lane writes the new fill back.  Only when
+        // some kind's segment overflows (once per 128 hits of that kind) does its first lane open a new one.
         const unsigned m0 = __ballot_sync(0xffffffffu, kind == 0), m1 = __ballot_sync(0xffffffffu, kind == 1),
                        m2 = __ballot_sync(0xffffffffu, kind == 2);
-        unsigned old_base = 0, old_fill = 0, new_base = 0;
-        if (lane < 3u && (m0 | m1 | m2) != 0u) {
-          const unsigned mk = lane == 0 ? m0 : (lane == 1 ? m1 : m2);
-          const unsigned cnt = (unsigned)__popc(mk);
-          const unsigned wsk = ws + (WS_SEG + 2u * lane) * 4u;
-          old_base = (unsigned)lds_i32(wsk), old_fill = (unsigned)lds_i32(wsk + 4u);
-          const unsigned room = (old_base == NO_SEG) ? 0u : (unsigned)SEG - old_fill;
-          if (cnt <= room) {
-            sts_i32(wsk + 4u, (int)(old_fill + cnt));
-          } else {  // open a new segment of this kind's queue; the old one is (or becomes) full
-            const unsigned sn = atomicAdd(&nseg_mat[lane], 1u);
-            if (old_base != NO_SEG) q0.seg_count[lane * (q_slots / SEG) + old_base / SEG] = SEG;
-            new_base = sn * SEG;
-            sts_i32(wsk, (int)new_base), sts_i32(wsk + 4u, (int)(cnt - room));
-          }
-        }
-        const unsigned kk = (unsigned)kind & 3u;
-        const unsigned ob = __shfl_sync(0xffffffffu, old_base, kk), of_ = __shfl_sync(0xffffffffu, old_fill, kk),
-                       nb = __shfl_sync(0xffffffffu, new_base, kk);
-        if (kind >= 0) {
+        if ((m0 | m1 | m2) != 0u) {
           const unsigned mk = kind == 0 ? m0 : (kind == 1 ? m1 : m2);
-          const unsigned rank = (unsigned)__popc(mk & lt_mask);
-          const unsigned room = (ob == NO_SEG) ? 0u : (unsigned)SEG - of_;
-          const unsigned dst = rank < room ? ob + of_ + rank : nb + (rank - room);
-          const unsigned e = (unsigned)kind * q_slots + dst;  // entry in the joint allocation
-          q0.A[e] = {r_fma(L.tbest, L.d.x, L.o.x), r_fma(L.tbest, L.d.y, L.o.y), r_fma(L.tbest, L.d.z, L.o.z), pv.w};
-          q0.B[e] = {L.d.x, L.d.y, L.d.z, lds_r(pay_r, R())};
-          q0.C[e] = {pv.x, pv.y, pv.z, i2r(L.best, R())};
+          const unsigned cnt = (unsigned)__popc(mk), rank = (unsigned)__popc(mk & lt_mask);
+          const unsigned kk = (unsigned)max(kind, 0);
+          const unsigned wsk = ws + (WS_SEG + 2u * kk) * 4u;
+          const unsigned base = (unsigned)lds_i32(wsk), fill = (unsigned)lds_i32(wsk + 4u);
+          const unsigned room = (base == NO_SEG) ? 0u : (unsigned)SEG - fill;
+          const bool over = kind >= 0 && cnt > room;
+          unsigned nb = 0;
+          if (__any_sync(0xffffffffu, over)) {
+            unsigned sn = 0;
+            if (over && rank == 0u) {  // this kind's first lane: the old segment is (or becomes) full, open the next:
+              if (base != NO_SEG) q0.seg_count[kk * (q_slots / SEG) + base / SEG] = SEG;
+              // the successor inside the group it was taken with, or SEG_GROUP fresh ones (the only atomic)
+              sn = seg_has_next(base) ? base / (unsigned)SEG + 1u : atomicAdd(&nseg_mat[kk], SEG_GROUP);
+            }
+            nb = __shfl_sync(0xffffffffu, sn, (__ffs((int)mk) - 1) & 31) * (unsigned)SEG;
+          }
+          __syncwarp();  // every lane has read (base, fill) before the first lanes update them
+          if (kind >= 0) {
+            if (rank == 0u) {
+              if (!over) sts_i32(wsk + 4u, (int)(fill + cnt));
+              else sts_i32(wsk, (int)nb), sts_i32(wsk + 4u, (int)(cnt - room));
+            }
+            const unsigned dst = rank < room ? base + fill + rank : nb + (rank - room);
+            const unsigned e = kk * q_slots + dst;  // entry in the joint allocation
+            Vec4<R> *qe = q0.A(e);  // one address, the fields at constant distances (segment-interleaved layout)
+            qe[0] = {r_fma(L.tbest, L.d.x, L.o.x), r_fma(L.tbest, L.d.y, L.o.y), r_fma(L.tbest, L.d.z, L.o.z), pv.w};
+            qe[SEG] = {L.d.x, L.d.y, L.d.z, lds_r(pay_r, R())};
+            qe[2 * SEG] = {pv.x, pv.y, pv.z, i2r(L.best, R())};
+          }
+          __syncwarp();
         }
-        __syncwarp();
       }
       if (done) L.cur = TRAV_IDLE;
     }
@@ -949,6 +985,8 @@ __global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, SM
       unsigned staged = (unsigned)lds_i32(ws + WS_STAGED * 4u);  // [next, staged) is in, or on its way into, the ring
       unsigned ib = 0, qb = 0;
       if (GEN) ib = (unsigned)lds_i32(ws + WS_IB * 4u), qb = (unsigned)lds_i32(ws + WS_QB * 4u);
+      const int root = lds_i32(ws + WS_ROOT * 4u);
+      const unsigned sp0r = (unsigned)lds_i32(sp0_slot);
       __syncwarp();
       unsigned idle_left = idle;
       for (;;) {
@@ -972,16 +1010,16 @@ __global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, SM
               const Vec4<R> pv = {R(1), R(1), R(1), i2r(pixel, R())};
               sts_vec4(pay_v, pv);
               sts_r(pay_r, i2r(offset, R()));
-              lane_init<R, UNIT>(L, V3<R>{R(0), R(0), R(0)}, dir, R(0), Lim<R>::tmax(), sp0, root);
+              lane_init<R, UNIT>(L, V3<R>{R(0), R(0), R(0)}, dir, R(0), Lim<R>::tmax(), sp0r, root);
             } else {
               const Vec4<R> A = lds_vec4(ring_a + (ray_i % RING) * VB, R()), B = lds_vec4(ring_b + (ray_i % RING) * VB, R());
               if (MODE == 0) {
                 // the payload, (attenuation, pixel) and the R2 offset, goes from the queue straight into this lane's slot
-                cp_async_vec4<R>(pay_v, rays.C + ray_i);
+                cp_async_vec4<R, 2>(pay_v, rays.A(ray_i));
                 sts_r(pay_r, B.w);
               }
               lane_init<R, UNIT>(L, V3<R>{A.x, A.y, A.z}, V3<R>{B.x, B.y, B.z}, (MODE == 0) ? R(0) : tmin_arg,
-                                 (MODE == 0) ? Lim<R>::tmax() : tmax_arg, sp0, root);
+                                 (MODE == 0) ? Lim<R>::tmax() : tmax_arg, sp0r, root);
             }
             // (Visiting the root right here, for all refilled lanes at once — broadcast shared-memory reads, no loop
             // iteration — was measured: +4.7 % trace time, profiles/README.md round 2.)
@@ -1063,8 +1101,9 @@ __global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, SM
               while (i >= (unsigned)gen.npix) i -= (unsigned)gen.npix;
               cp_async_scalar(ring_a + (e % RING) * 4u, reinterpret_cast<const float *>(gen.pixel_list + i));
             } else {
-              cp_async_vec4<R>(ring_a + (e % RING) * VB, rays.A + e);
-              cp_async_vec4<R>(ring_b + (e % RING) * VB, rays.B + e);
+              const Vec4<R> *src = rays.A(e);
+              cp_async_vec4<R, 0>(ring_a + (e % RING) * VB, src);
+              cp_async_vec4<R, 1>(ring_b + (e % RING) * VB, src);
             }
           }
           if (staged < upto) staged = upto;
@@ -1157,9 +1196,10 @@ __global__ void __launch_bounds__(256)
     decode(w, m, seg, i0);
     const unsigned i = (unsigned)m * q_slots + seg * SEG + i0 + lane;  // entry in the joint allocation
     const unsigned dst = slot0 + buf * bufsz;
-    cp_async_vec4<R>(dst, q0.A + i);
-    cp_async_vec4<R>(dst + arr, q0.B + i);
-    cp_async_vec4<R>(dst + 2u * arr, q0.C + i);
+    const Vec4<R> *src = q0.A(i);
+    cp_async_vec4<R, 0>(dst, src);
+    cp_async_vec4<R, 1>(dst + arr, src);
+    cp_async_vec4<R, 2>(dst + 2u * arr, src);
     if (lane == 0)
       cp_async_scalar(cnt0 + buf * 4u, reinterpret_cast<const float *>(q0.seg_count + (unsigned)m * (q_slots / SEG) + seg));
   };
@@ -1388,9 +1428,10 @@ __global__ void __launch_bounds__(256)
     }
     const unsigned dst = seg_append(alive, ob, of, nseg_out, out.seg_count, lane, lt_mask);
     if (alive) {
-      out.A[dst] = {no.x, no.y, no.z, R(0)};
-      out.B[dst] = {nd.x, nd.y, nd.z, B.w};
-      out.C[dst] = {nattn.x, nattn.y, nattn.z, A.w};
+      Vec4<R> *oe = out.A(dst);
+      oe[0] = {no.x, no.y, no.z, R(0)};
+      oe[SEG] = {nd.x, nd.y, nd.z, B.w};
+      oe[2 * SEG] = {nattn.x, nattn.y, nattn.z, A.w};
     }
    }
   }
@@ -1506,8 +1547,9 @@ template <class R>
 __global__ void k_pack_rays(const float *__restrict__ o, const float *__restrict__ d, long long n, Queue<R> q) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  q.A[i] = {R(o[3 * i]), R(o[3 * i + 1]), R(o[3 * i + 2]), R(0)};
-  q.B[i] = {R(d[3 * i]), R(d[3 * i + 1]), R(d[3 * i + 2]), R(0)};
+  Vec4<R> *e = q.A((unsigned)i);
+  e[0] = {R(o[3 * i]), R(o[3 * i + 1]), R(o[3 * i + 2]), R(0)};
+  e[SEG] = {R(d[3 * i]), R(d[3 * i + 1]), R(d[3 * i + 2]), R(0)};
   if (i % SEG == 0) q.seg_count[i / SEG] = (int32_t)(n - i < SEG ? n - i : SEG);  // dense
 }
 

@@ -35,11 +35,11 @@ struct Tables {
 };
 // producer warps that may each leave one partially filled segment behind in a queue (upper bound over
 // every launch shape used here), i.e. the slack a segmented queue needs on top of its dense capacity
-constexpr size_t MAX_PRODUCER_WARPS = 16384;
+constexpr size_t MAX_PRODUCER_WARPS = 8192;
 template <class R>
 struct Work {
-  Queue<R> rays{nullptr, nullptr, nullptr, nullptr};
-  Queue<R> mq{nullptr, nullptr, nullptr, nullptr};  // the NUM_MAT_KINDS hit queues: equal slices of one allocation
+  Queue<R> rays{nullptr, nullptr};
+  Queue<R> mq{nullptr, nullptr};  // the NUM_MAT_KINDS hit queues: equal slices of one allocation
   size_t slots = 0;                                   // entries per queue (a multiple of SEG)
   size_t cap = 0;                                     // rays per batch the queues were sized for
 };
@@ -133,8 +133,8 @@ static void free_tables(Tables<R> &t) {
 }
 template <class R>
 static void free_queue(Queue<R> &q) {
-  cudaFree(q.A), cudaFree(q.B), cudaFree(q.C), cudaFree(q.seg_count);
-  q = Queue<R>{nullptr, nullptr, nullptr, nullptr};
+  cudaFree(q.base), cudaFree(q.seg_count);
+  q = Queue<R>{nullptr, nullptr};
 }
 template <class R>
 static void free_work(Work<R> &w) {
@@ -280,11 +280,10 @@ static int ensure_work(DevicePool *d, size_t cap) {
   Work<R> &w = d->work<R>();
   if (w.cap >= cap) return PTB_OK;
   free_work(w);
-  const size_t segs = (cap + SEG - 1) / SEG + MAX_PRODUCER_WARPS, slots = segs * SEG;
+  // (a producer warp may leave one partly filled and SEG_GROUP - 1 unopened segments behind per queue)
+  const size_t segs = (cap + SEG - 1) / SEG + SEG_GROUP * MAX_PRODUCER_WARPS, slots = segs * SEG;
   auto alloc_q = [&](Queue<R> &q, size_t n) -> int {
-    CK(cudaMalloc((void **)&q.A, n * slots * sizeof(Vec4<R>)));
-    CK(cudaMalloc((void **)&q.B, n * slots * sizeof(Vec4<R>)));
-    CK(cudaMalloc((void **)&q.C, n * slots * sizeof(Vec4<R>)));
+    CK(cudaMalloc((void **)&q.base, 3 * n * slots * sizeof(Vec4<R>)));  // segment-interleaved A, B, C (device_types.cuh)
     CK(cudaMalloc((void **)&q.seg_count, n * segs * sizeof(int32_t)));
     return PTB_OK;
   };
@@ -365,7 +364,8 @@ static DScene<R> make_dscene(ptb_scene *s, size_t *scene_bytes_out) {
   sc.stack_cap = std::min(std::max(s->bvh.max_stack + 1, 4), 97);
   sc.scene_in_smem = (bytes <= 100 * 1024 && s->bvh.max_stack + 1 <= sc.stack_cap) ? 1 : 0;
   sc.bg_kind = s->host.bg_kind;
-  for (int i = 0; i < 3; ++i) sc.bg0[i] = (R)s->host.bg0[i], sc.bg1[i] = (R)s->host.bg1[i];
+  for (int i = 0; i < 3; ++i)
+    sc.bg0[i] = (R)s->host.bg0[i], sc.bg1[i] = (R)s->host.bg1[i], sc.bgd[i] = (R)(s->host.bg1[i] - s->host.bg0[i]);
   sc.has_light = s->host.has_light ? 1 : 0;
   sc.has_emissive = s->host.has_emissive() ? 1 : 0;
   for (int i = 0; i < 3; ++i)
@@ -1487,9 +1487,8 @@ int ptb_raygen(const ptb_params *p, int64_t first, int64_t n, int32_t *pixel, in
   const size_t nn = (size_t)std::max<int64_t>(n, 1);
   Queue<float> q;
   double *d_cx = nullptr, *d_cy = nullptr;
-  CK(cudaMalloc((void **)&q.A, nn * 16));
-  CK(cudaMalloc((void **)&q.B, nn * 16));
-  CK(cudaMalloc((void **)&q.C, nn * 16));
+  const size_t nseg_q = nn / SEG + 1;
+  CK(cudaMalloc((void **)&q.base, 3 * nseg_q * SEG * 16));
   CK(cudaMalloc((void **)&q.seg_count, (nn / SEG + 1) * sizeof(int32_t)));
   CK(cudaMalloc((void **)&d_cx, nn * 8));
   CK(cudaMalloc((void **)&d_cy, nn * 8));
@@ -1498,9 +1497,12 @@ int ptb_raygen(const ptb_params *p, int64_t first, int64_t n, int32_t *pixel, in
     k_raygen<float><<<(unsigned)((n + 255) / 256), 256>>>(make_gen(rcst, tmp.pixel_list, pass0, i0), (unsigned)n, q, d_cx, d_cy);
   }
   CK(cudaGetLastError());
-  std::vector<Vec4<float>> A(nn), B(nn);  // A: the entry's C (attenuation, pixel)
-  CK(cudaMemcpy(A.data(), q.C, (size_t)n * 16, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(B.data(), q.B, (size_t)n * 16, cudaMemcpyDeviceToHost));
+  std::vector<Vec4<float>> all(3 * nseg_q * SEG), A(nn), B(nn);  // A: the entry's C (attenuation, pixel)
+  CK(cudaMemcpy(all.data(), q.base, all.size() * 16, cudaMemcpyDeviceToHost));
+  for (int64_t i = 0; i < n; ++i) {
+    const size_t at = Queue<float>::idx((unsigned)i);
+    A[i] = all[at + 2 * SEG], B[i] = all[at + SEG];
+  }
   if (cx) CK(cudaMemcpy(cx, d_cx, (size_t)n * 8, cudaMemcpyDeviceToHost));
   if (cy) CK(cudaMemcpy(cy, d_cy, (size_t)n * 8, cudaMemcpyDeviceToHost));
   for (int64_t i = 0; i < n; ++i) {
@@ -1511,7 +1513,7 @@ int ptb_raygen(const ptb_params *p, int64_t first, int64_t n, int32_t *pixel, in
     if (offset) offset[i] = oi;
     if (dir_xyz) dir_xyz[3 * i] = B[i].x, dir_xyz[3 * i + 1] = B[i].y, dir_xyz[3 * i + 2] = B[i].z;
   }
-  cudaFree(q.A), cudaFree(q.B), cudaFree(q.C), cudaFree(q.seg_count), cudaFree(d_cx), cudaFree(d_cy);
+  cudaFree(q.base), cudaFree(q.seg_count), cudaFree(d_cx), cudaFree(d_cy);
   return PTB_OK;
 }
 
