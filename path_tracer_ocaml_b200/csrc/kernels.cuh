@@ -334,6 +334,42 @@ __device__ __forceinline__ void cp_async_vec4(unsigned saddr, const Vec4<R> *g) 
   cp_async16_off<FIELD * SEG * (int)sizeof(Vec4<R>)>(saddr, g);
   if constexpr (sizeof(Vec4<R>) == 32) cp_async16_off<FIELD * SEG * (int)sizeof(Vec4<R>) + 16>(saddr + 16u, g);
 }
+// Bulk asynchronous copies (sm_90+/sm_100: the TMA unit's 1-D form, SASS UBLKCP) and the mbarrier that tracks them.
+// One lane moves a whole contiguous run — 512 B of one field of 32 queue entries — with one instruction, instead of 32
+// lanes moving 16 B each.
+__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned mbar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(mbar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned sdst, const void *gsrc, unsigned bytes, unsigned mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sdst), "l"(gsrc),
+               "r"(bytes), "r"(mbar)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *gdst, unsigned ssrc, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // traversal-stack entry = (child ref, t_near): 8 B in float (one 64-bit shared access), 16 B in double
 __device__ __forceinline__ void stk_store(unsigned addr, int ref, float t) {
   asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(ref), "r"(__float_as_int(t)));
@@ -1154,12 +1190,24 @@ __global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, SM
 
 // Stage 4 — material scatter.  Work item = one warp-sized chunk of ONE material's hit queue, so the
 // material switch below is warp-uniform.
-constexpr unsigned SHADE_NBUF = 3;  // staging buffers per thread: SHADE_NBUF - 1 items in flight while one is shaded
+#ifndef PTB_SHADE_NBUF
+#define PTB_SHADE_NBUF 3
+#endif
+constexpr unsigned SHADE_NBUF = PTB_SHADE_NBUF;  // staging buffers per thread: SHADE_NBUF - 1 items in flight while one is shaded
 template <class R>
-__host__ __device__ constexpr size_t shade_smem_bytes(unsigned block) {
-  return (size_t)SHADE_NBUF * (3u * block * sizeof(Vec4<R>) + (block / 32u) * 4u);
+__host__ __device__ constexpr size_t shade_smem_bytes(unsigned block, bool bulk = false) {
+  // BULK, per warp: SHADE_NBUF buffers of [A x 32][B x 32][C x 32], then the mbarriers (64 B)
+  return bulk ? (size_t)(block / 32u) * (SHADE_NBUF * 96u * sizeof(Vec4<R>) + 64u)
+              : (size_t)SHADE_NBUF * (3u * block * sizeof(Vec4<R>) + (block / 32u) * 4u);
 }
-template <class R>
+// BULK: the entries of a work item come in with bulk asynchronous copies (the TMA unit's 1-D form, SASS UBLKCP): one
+// lane issues three 512-byte copies — the item's A, B and C runs, contiguous in the segment-interleaved layout —
+// tracked by an mbarrier, instead of 32 lanes issuing three 16-byte cp.async each (96 requests -> 3).  Measured on
+// the 4K frame (profiles/README.md, round 2): 0.82 -> 0.91 of the HBM copy bandwidth, and the bounce-0 launch no
+// longer wants fewer blocks than the others.  The outgoing rays stay per-lane 16-byte stores: staging them in shared
+// memory for bulk stores was measured too and is slower (two more warp syncs and a proxy fence per item:
+// profiles/experiments/r2_kshade_bulk_in_and_out.patch).
+template <class R, bool BULK>
 __global__ void __launch_bounds__(256)
     k_shade(DScene<R> sc, RenderConst rc, int bounce, Queue<R> q0, unsigned q_slots,
             unsigned *__restrict__ nseg_mat, Queue<R> out, unsigned *__restrict__ nseg_out, R *__restrict__ sums, int last) {
@@ -1182,6 +1230,20 @@ __global__ void __launch_bounds__(256)
   const unsigned sbase = (unsigned)__cvta_generic_to_shared(shade_smem);
   const unsigned slot0 = sbase + threadIdx.x * VB, bufsz = 3u * blockDim.x * VB, arr = blockDim.x * VB;
   const unsigned cnt0 = sbase + SHADE_NBUF * bufsz + (threadIdx.x >> 5) * (SHADE_NBUF * 4u);
+  // BULK layout of this warp's region
+  constexpr unsigned IBUF = 96u * VB;  // one buffer: three fields x 32 entries
+  const unsigned wbase = sbase + (threadIdx.x >> 5) * (SHADE_NBUF * IBUF + 64u);
+  const unsigned mbar0 = wbase + SHADE_NBUF * IBUF;
+  unsigned fill[SHADE_NBUF - 1];  // BULK, lane 0: fill counts of the segments of the items in flight
+  unsigned parity = 0u;
+  if constexpr (BULK) {
+    if (lane == 0) {
+#pragma unroll
+      for (unsigned b = 0; b < SHADE_NBUF; ++b) mbar_init(mbar0 + 8u * b, 1u);
+      mbar_fence_init();
+    }
+    __syncwarp();
+  }
   // item -> (material, segment, first entry)
   auto decode = [&](unsigned w, int &m, unsigned &seg, unsigned &i0) {
     seg = w / (SEG / 32);
@@ -1190,10 +1252,23 @@ __global__ void __launch_bounds__(256)
     else if (seg < c0 + c1) m = 1, seg -= c0;
     else m = 2, seg -= c0 + c1;
   };
-  auto prefetch = [&](unsigned w, unsigned buf) {
+  auto prefetch = [&](unsigned w, unsigned buf) -> unsigned {
     int m;
     unsigned seg, i0;
     decode(w, m, seg, i0);
+    if constexpr (BULK) {
+      unsigned f = 0;
+      if (lane == 0) {
+        const Vec4<R> *src = q0.A((unsigned)m * q_slots + seg * SEG + i0);
+        const unsigned dst = wbase + buf * IBUF, mb = mbar0 + 8u * buf;
+        mbar_expect_tx(mb, IBUF);
+        bulk_g2s(dst, src, 32u * VB, mb);
+        bulk_g2s(dst + 32u * VB, src + SEG, 32u * VB, mb);
+        bulk_g2s(dst + 64u * VB, src + 2 * SEG, 32u * VB, mb);
+        f = (unsigned)__ldg(q0.seg_count + (unsigned)m * (q_slots / SEG) + seg);
+      }
+      return f;
+    }
     const unsigned i = (unsigned)m * q_slots + seg * SEG + i0 + lane;  // entry in the joint allocation
     const unsigned dst = slot0 + buf * bufsz;
     const Vec4<R> *src = q0.A(i);
@@ -1202,6 +1277,7 @@ __global__ void __launch_bounds__(256)
     cp_async_vec4<R, 2>(dst + 2u * arr, src);
     if (lane == 0)
       cp_async_scalar(cnt0 + buf * 4u, reinterpret_cast<const float *>(q0.seg_count + (unsigned)m * (q_slots / SEG) + seg));
+    return 0u;
   };
   // Items are handed out dynamically, a few at a time (nseg_mat[3] is the launch's cursor): the SMs do not all get
   // the same share of the memory system (GPCs differ in size), and with a static split the slowest ones set
@@ -1230,28 +1306,38 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
   for (unsigned k = 0; k + 1 < SHADE_NBUF; ++k) {
     ids[k] = next_item();
-    if (ids[k] != NONE) prefetch(ids[k], k);
-    cp_async_commit();
+    fill[k] = 0u;
+    if (ids[k] != NONE) fill[k] = prefetch(ids[k], k);
+    if (!BULK) cp_async_commit();
   }
   unsigned buf = 0;
   while (ids[0] != NONE) {
     __syncwarp();  // every lane is done with the buffer of the item before, which is filled next
     const unsigned w = ids[0];
+    const unsigned fw = fill[0];
 #pragma unroll
-    for (unsigned k = 0; k + 2 < SHADE_NBUF; ++k) ids[k] = ids[k + 1];
+    for (unsigned k = 0; k + 2 < SHADE_NBUF; ++k) ids[k] = ids[k + 1], fill[k] = fill[k + 1];
     {
       const unsigned wn = next_item();
       ids[SHADE_NBUF - 2] = wn;
-      if (wn != NONE) prefetch(wn, buf == 0u ? SHADE_NBUF - 1u : buf - 1u);
+      fill[SHADE_NBUF - 2] = 0u;
+      if (wn != NONE) fill[SHADE_NBUF - 2] = prefetch(wn, buf == 0u ? SHADE_NBUF - 1u : buf - 1u);
     }
-    cp_async_commit();
-    cp_async_wait<SHADE_NBUF - 1>();  // item w has landed
-    __syncwarp();        // (lane 0 copied the count for the warp)
     int m;
     unsigned seg, i0;
     decode(w, m, seg, i0);
     const unsigned cbuf = buf;
-    const unsigned nm = (unsigned)lds_i32(cnt0 + cbuf * 4u);  // valid entries of the item's segment
+    unsigned nm;
+    if constexpr (BULK) {
+      mbar_wait(mbar0 + 8u * cbuf, (parity >> cbuf) & 1u);  // item w has landed
+      parity ^= 1u << cbuf;
+      nm = __shfl_sync(0xffffffffu, fw, 0);
+    } else {
+      cp_async_commit();
+      cp_async_wait<SHADE_NBUF - 1>();  // item w has landed
+      __syncwarp();                     // (lane 0 copied the count for the warp)
+      nm = (unsigned)lds_i32(cnt0 + cbuf * 4u);  // valid entries of the item's segment
+    }
     buf = buf + 1u == SHADE_NBUF ? 0u : buf + 1u;
     if (i0 >= nm) continue;
    {
@@ -1260,10 +1346,11 @@ __global__ void __launch_bounds__(256)
     V3<R> no = {R(0), R(0), R(0)}, nd = {R(0), R(0), R(1)}, nattn = {R(0), R(0), R(0)};
     Vec4<R> A = {R(0), R(0), R(0), R(0)}, B = A;
     if (valid) {
-      const unsigned src = slot0 + cbuf * bufsz;
+      const unsigned src = BULK ? wbase + cbuf * IBUF + lane * VB : slot0 + cbuf * bufsz;
+      const unsigned fstride = BULK ? 32u * VB : arr;
       A = lds_vec4(src, R());
-      B = lds_vec4(src + arr, R());
-      const Vec4<R> C = lds_vec4(src + 2u * arr, R());
+      B = lds_vec4(src + fstride, R());
+      const Vec4<R> C = lds_vec4(src + 2u * fstride, R());
       V3<R> p = {A.x, A.y, A.z};
       const V3<R> d = {B.x, B.y, B.z};
       const int offset = r2i(B.w);
@@ -1426,12 +1513,14 @@ __global__ void __launch_bounds__(256)
       nd = quat_transform(frame_inv, dir_ss);
       no = {r_fma(nd.x, R(1e-3), p.x), r_fma(nd.y, R(1e-3), p.y), r_fma(nd.z, R(1e-3), p.z)};
     }
-    const unsigned dst = seg_append(alive, ob, of, nseg_out, out.seg_count, lane, lt_mask);
-    if (alive) {
-      Vec4<R> *oe = out.A(dst);
-      oe[0] = {no.x, no.y, no.z, R(0)};
-      oe[SEG] = {nd.x, nd.y, nd.z, B.w};
-      oe[2 * SEG] = {nattn.x, nattn.y, nattn.z, A.w};
+    {
+      const unsigned dst = seg_append(alive, ob, of, nseg_out, out.seg_count, lane, lt_mask);
+      if (alive) {
+        Vec4<R> *oe = out.A(dst);
+        oe[0] = {no.x, no.y, no.z, R(0)};
+        oe[SEG] = {nd.x, nd.y, nd.z, B.w};
+        oe[2 * SEG] = {nattn.x, nattn.y, nattn.z, A.w};
+      }
     }
    }
   }

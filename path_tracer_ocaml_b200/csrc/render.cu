@@ -532,19 +532,22 @@ static int render_impl(ptb_scene *s, const ptb_params &p, R *d_sums, cudaStream_
   CK(cudaMemsetAsync(ctl, 0, sizeof(Ctl), st));
   CK(cudaEventRecord(e0, st));
   uint64_t launches = 0;
-  const size_t shade_smem = shade_smem_bytes<R>(256);  // staging buffers of (A, B, C) per thread + fill counts
-  CK(cudaFuncSetAttribute(k_shade<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shade_smem));
+  // queue entries move with bulk asynchronous copies (PTB_SHADE_BULK=0: the per-lane cp.async path, kept for A/B runs)
+  static const bool shade_bulk = !(std::getenv("PTB_SHADE_BULK") && std::atoi(std::getenv("PTB_SHADE_BULK")) == 0);
+  const size_t shade_smem = shade_smem_bytes<R>(256, shade_bulk);  // staging buffers of (A, B, C) + fill counts / mbarriers
+  CK(cudaFuncSetAttribute(k_shade<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shade_smem_bytes<R>(256, true)));
+  CK(cudaFuncSetAttribute(k_shade<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shade_smem_bytes<R>(256, false)));
   int shade_per_sm = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&shade_per_sm, k_shade<R>, 256, shade_smem));
+  if (shade_bulk) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&shade_per_sm, k_shade<R, true>, 256, shade_smem));
+  else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&shade_per_sm, k_shade<R, false>, 256, shade_smem));
   if (const char *e = std::getenv("PTB_SHADE_BLOCKS")) shade_per_sm = std::min(shade_per_sm, std::max(1, std::atoi(e)));
   const int shade_grid = d->sm_count * std::max(shade_per_sm, 1);
-  // The bounce-0 launch is different: camera hits are coherent (a warp's 32 hits are one or two primitives), the
-  // table look-ups cost nothing and the launch is bound by the memory system alone — which delivers LESS when
-  // more warps stream through it at once (measured on the 4K frame: 5.48 / 4.44 / 3.89 / 6.41 ms with 4 / 3 / 2 / 1
-  // blocks per SM), while the later, incoherent launches need all the warps they can get to hide their look-ups
-  // (1.6 ms with 4 blocks, 2.0 ms with 2).  Small batches (< 16 Mi paths) do not congest it: they keep 4 too.
-  int shade_per_sm0 = std::min(shade_per_sm, 2);
-  if (const char *e = std::getenv("PTB_SHADE_BLOCKS0")) shade_per_sm0 = std::min(shade_per_sm, std::max(1, std::atoi(e)));
+  // With per-lane cp.async input (PTB_SHADE_BULK=0) the bounce-0 launch of a big batch wants fewer blocks: its hits
+  // are coherent, the table look-ups cost nothing, and the memory system delivers LESS when more warps stream 16-byte
+  // requests through it (5.48 / 4.44 / 3.89 / 6.41 ms with 4 / 3 / 2 / 1 blocks per SM), while the later, incoherent
+  // launches need every warp to hide their look-ups.  With bulk copies (3 requests of 512 B per item instead of 96
+  // of 16 B) that congestion is gone and every launch runs best with all the blocks that fit.
+  int shade_per_sm0 = shade_bulk ? shade_per_sm : std::min(shade_per_sm, 2);
   const int shade_grid0 = d->sm_count * std::max(shade_per_sm0, 1);
   for (long long first = 0; first < total; first += (long long)NB) {
     const unsigned n = (unsigned)std::min<long long>((long long)NB, total - first);
@@ -567,8 +570,13 @@ static int render_impl(ptb_scene *s, const ptb_params &p, R *d_sums, cudaStream_
       if (!last || emissive) {
         // a path that is still alive after the last allowed bounce contributes black (integrator.ml:31-32), so the
         // last bounce needs no scatter — unless the scene has emitters, whose emission k_shade collects (last = 1)
-        k_shade<R><<<(b == 0 && n >= (1u << 24)) ? shade_grid0 : shade_grid, 256, shade_smem, st>>>(sc, rcst, b, w.mq, (unsigned)w.slots, &ctl->nseg_mat[b][0], w.rays,
-                                               &ctl->nseg_rays[b + 1], d_sums, last ? 1 : 0);
+        const int sg = (b == 0 && n >= (1u << 24)) ? shade_grid0 : shade_grid;
+        if (shade_bulk)
+          k_shade<R, true><<<sg, 256, shade_smem, st>>>(sc, rcst, b, w.mq, (unsigned)w.slots, &ctl->nseg_mat[b][0], w.rays,
+                                                          &ctl->nseg_rays[b + 1], d_sums, last ? 1 : 0);
+        else
+          k_shade<R, false><<<sg, 256, shade_smem, st>>>(sc, rcst, b, w.mq, (unsigned)w.slots, &ctl->nseg_mat[b][0], w.rays,
+                                                           &ctl->nseg_rays[b + 1], d_sums, last ? 1 : 0);
         ++launches;
       }
     }
