@@ -18,6 +18,10 @@
 #pragma once
 #include <cfloat>
 
+#ifndef PTB_GLOBAL_BLOCKS
+#define PTB_GLOBAL_BLOCKS 4  // resident 256-thread blocks per SM of the global-memory traversal kernel: 64 registers
+                             // per thread, no spills (3 blocks / 70 registers: -13 % on the C5 triangle soup; 5 / 48: spills)
+#endif
 #ifndef PTB_STACK_HOT
 #define PTB_STACK_HOT 12  // shared-memory levels of the hybrid traversal stack (global-memory scenes)
 #endif
@@ -817,7 +821,8 @@ __global__ void __launch_bounds__(256) k_raygen(GenConst g, unsigned n, Queue<R>
 // Incoming rays never wait on HBM/L2: each warp keeps the next RING entries (origin, direction) of its claimed
 // chunk in flight into its staging ring (cp.async issued one refill ahead), and the payload of a ray goes
 // straight from the queue into the lane's payload slot (cp.async, first read at the lane's flush).
-constexpr int LEAF_MIN = 8;  // lanes holding a leaf before the warp runs the leaf phase (tuned: 6..12 equal, 1: -4 %)
+constexpr int LEAF_MIN = 8;  // lanes holding a leaf before the warp runs the leaf phase (tuned: 6..12 equal, 1: -4 %;
+                             // global-memory triangle scenes measured with 8 / 12 / 16 / 20 / 24: best at 8..12)
 constexpr unsigned WS_NEXT = 0, WS_END = 1, WS_FETCHED = 2, WS_SEG = 3 /* base,fill x 3 kinds */, WS_STAGED = 9,
                    WS_REM_BASE = 10, WS_REM_CNT = 11 /* whole segments claimed but not opened yet */,
                    WS_SEEN = 12 /* the cursor at the last claim */, WS_IB = 13, WS_QB = 14 /* GEN: pixel-list index and
@@ -837,7 +842,7 @@ __host__ __device__ constexpr size_t trace_smem_per_thread(int stack_cap, bool s
 // BLK: the block size when it is known at compile time (the 1024-thread float launch of shared-memory scenes: the
 // stack's level stride becomes an immediate), 0 = blockDim.x.
 template <class R, int MODE, bool SMEM, bool GEN, int BLK = 0>
-__global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, SMEM ? 1 : (sizeof(R) == 8 ? 1 : 3))
+__global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, SMEM ? 1 : (sizeof(R) == 8 ? 1 : PTB_GLOBAL_BLOCKS))
     k_trace(DScene<R> sc, GenConst gen, unsigned gen_n, Queue<R> rays, const unsigned *__restrict__ nseg_ptr, unsigned nseg_imm,
             unsigned *__restrict__ cursor, int refill_below, Queue<R> q0, unsigned q_slots,
             unsigned *__restrict__ nseg_mat, unsigned *__restrict__ n_traced, int enqueue_hits, R *__restrict__ sums,
