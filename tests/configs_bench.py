@@ -29,7 +29,57 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-def render_config(name, make_scene, W, H, spp, mb, small, reps=3):
+C_BOX, C_SPH, C_TRI, C_HIT, C_FILM = 25.0, 34.0, 46.0, 200.0, 27.0  # algorithmic lane-ops per unit
+_PEAK = {}
+
+
+def fp32_peak():
+    """Measured FFMA issue rate of this GPU in lane-op/s (the roofline denominator, as in bench.py)."""
+    if "v" not in _PEAK:
+        import ctypes as C
+        v = C.c_double(0)
+        capi.check(P.lib().ptb_fp32_peak(0, C.byref(v), None))
+        _PEAK["v"] = v.value * 1e12
+    return _PEAK["v"]
+
+
+def hbm_peak():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] * 1e9
+    except Exception:
+        return 6650e9
+
+
+def bytes_per_ray(*keys):
+    """ncu-measured DRAM bytes per ray of the traversal kernel (profiles/r2_triangle_bytes_per_ray.json), mean of keys."""
+    try:
+        e = json.load(open(os.path.join(ROOT, "profiles", "r2_triangle_bytes_per_ray.json")))["entries"]
+        return float(np.mean([e[k]["dram_bytes_per_ray"] for k in keys]))
+    except Exception:
+        return None
+
+
+def roofline(rays_per_s, cn, b_dram):
+    """bound = min(P_issue / A_ray, BW_hbm / B_ray); A_ray from the oracle's reference-faithful counts of
+    the same rays (box x 25 + sphere x 34 + triangle x 46 lane-ops), B_ray = DRAM bytes per ray measured with ncu."""
+    rays = max(int(cn.rays), 1)
+    a = (cn.box_tests * C_BOX + cn.sphere_tests * C_SPH + cn.tri_tests * C_TRI) / rays
+    issue = fp32_peak() / a if a > 0 else None
+    hbm = hbm_peak() / b_dram if b_dram else None
+    bound = min(x for x in (issue, hbm) if x is not None)
+    return {"a_ray_lane_ops": a, "box_per_ray": cn.box_tests / rays, "sphere_per_ray": cn.sphere_tests / rays,
+            "tri_per_ray": cn.tri_tests / rays, "b_ray_dram_bytes": b_dram, "issue_bound_rays_per_s": issue,
+            "hbm_bound_rays_per_s": hbm, "bound": "fp32_issue" if bound == issue else "hbm", "bound_rays_per_s": bound,
+            "achieved_rays_per_s": rays_per_s, "frac": rays_per_s / bound}
+
+
+def pinned_like(a):
+    b = capi.pinned_empty(a.shape, a.dtype)
+    b[...] = a
+    return b
+
+
+def render_config(name, make_scene, W, H, spp, mb, small, reps=3, bkeys=None):
     scene = make_scene(W, H)
     integ = P.Integrator(scene, W, H, spp, mb, device=0)
     tree = scene.tree_stats()
@@ -56,6 +106,8 @@ def render_config(name, make_scene, W, H, spp, mb, small, reps=3):
                      "within_tol": float(np.mean(np.abs(d) <= 0.02 * np.abs(ref) + 1 / 255)),
                      "bias": float(np.abs(d.mean((0, 1))).max()), "rays_device": int(i2.stats.rays), "rays_oracle": int(cn.rays),
                      "oracle_mpaths_per_s": cn.paths / dt / 1e6, "oracle_threads": os.cpu_count()}
+    # trace kernel alone against its bound (the oracle's per-ray test counts of the reduced-size render of the scene)
+    out["roofline_trace"] = roofline(best["rays"] / (best["ms_trace"] * 1e-3), cn, bytes_per_ray(*bkeys) if bkeys else None)
     log(json.dumps(out))
     return out
 
@@ -82,7 +134,7 @@ def sweep(quick):
     res = []
     n_list = [1 << 20, 1 << 24] if quick else [1 << 20, 1 << 22, 1 << 24, 1 << 26]
     scenes = [("spheres", m) for m in (4, 16, 64, 256, 1024, 4096)] + [("triangles", t) for t in
-                                                                      ((10_000, 100_000) if quick else (10_000, 100_000, 1_000_000))]
+                                                                      ((10_000, 100_000) if quick else (10_000, 100_000, 1_000_000, 10_000_000))]
     lo, hi = np.full(3, -10.0), np.full(3, 10.0)
     for kind, m in scenes:
         s = P.Scene()
@@ -100,32 +152,64 @@ def sweep(quick):
         t0 = time.perf_counter()
         s.commit(0)
         commit_ms = (time.perf_counter() - t0) * 1e3
-        osc = O.OracleScene(s.tables())
+        # the reference's tree over 10^7 triangles is out of reach for the CPU side of a sweep: GPU numbers only there
+        osc = O.OracleScene(s.tables()) if m <= 1_000_000 else None
+        import torch
+        import ctypes as C
         for coherent in (True, False):
-            for n in n_list:
-                o, d = rays_for(rng, n, lo, hi, coherent)
-                best = None
+            ns_list = n_list if m <= 1_000_000 else [1 << 22]
+            if kind == "spheres" and m in (64, 1024) and not quick:
+                ns_list = n_list + [1 << 28]  # BASELINE's upper end on the ray axis
+            for n in ns_list:
+                base = min(n, 1 << 24)  # 2^28 rays = 2^24 distinct rays, 16 times over (generation time, not the device, bounds this)
+                o0, d0 = rays_for(rng, base, lo, hi, coherent)
+                o, d = capi.pinned_empty((n, 3), np.float32), capi.pinned_empty((n, 3), np.float32)
+                for k in range(n // base):
+                    o[k * base:(k + 1) * base], d[k * base:(k + 1) * base] = o0, d0
+                t, p = capi.pinned_empty(n, np.float32), capi.pinned_empty(n, np.int32)
+                # (a) through the C ABI with page-locked HOST buffers: chunk-pipelined copies + kernels, wall clock
+                host_ms = None
                 for _ in range(3):
                     st = capi.Stats()
-                    t, p = intersect_batch(s, o, d, 0.0, 3.0e38, stats=st)
-                    if best is None or st.ms_device < best[0]:
-                        best = (st.ms_device, st.ms_total)
+                    capi.check(P.lib().ptb_intersect_batch(s.h, capi.fptr(o), capi.fptr(d), 0.0, 3.0e38, n, capi.fptr(t), capi.iptr(p), 0, C.byref(st)))
+                    host_ms = st.ms_total if host_ms is None else min(host_ms, st.ms_total)
+                # (b) device-resident: rays and results already in HBM
+                m_dev = min(n, 1 << 26)
+                do, dd = torch.from_numpy(o[:m_dev]).cuda(), torch.from_numpy(d[:m_dev]).cuda()
+                dt_, dp_ = torch.empty(m_dev, device="cuda"), torch.empty(m_dev, dtype=torch.int32, device="cuda")
+                dev_ms = None
+                for _ in range(3):
+                    st = capi.Stats()
+                    capi.check(P.lib().ptb_intersect_batch_device(s.h, C.c_void_p(do.data_ptr()), C.c_void_p(dd.data_ptr()), 0.0, 3.0e38, m_dev,
+                                                                  C.c_void_p(dt_.data_ptr()), C.c_void_p(dp_.data_ptr()), 0, None, C.byref(st)))
+                    dev_ms = st.ms_device if dev_ms is None else min(dev_ms, st.ms_device)
+                del do, dd, dt_, dp_
                 row = {"prims": kind, "m": m, "rays": n, "coherent": coherent, "commit_ms": commit_ms,
-                       "gpu_mrays_per_s_device": n / best[0] / 1e3, "gpu_mrays_per_s_host_buffers": n / best[1] / 1e3,
-                       "hit_fraction": float(np.mean(p >= 0))}
-                # CPU side on a bounded sample: the oracle's reference-faithful tree + leaf kernels
-                ns = min(n, 1 << 18)
-                t0 = time.perf_counter()
-                t_ref, p_ref, _ = osc.intersect_batch(o[:ns], d[:ns], 0.0, 3.0e38, n_threads=os.cpu_count())
-                dt = time.perf_counter() - t0
-                row["cpu_mrays_per_s"] = ns / dt / 1e6
-                row["cpu_sample_rays"] = ns
-                row["cpu_threads"] = os.cpu_count()
-                row["prim_agreement"] = float(np.mean(p[:ns] == p_ref))
-                hit = (p[:ns] == p_ref) & (p_ref >= 0)
-                row["t_rel_err_p99"] = float(np.quantile(np.abs(t[:ns][hit] - t_ref[hit]) / t_ref[hit], 0.99)) if hit.any() else 0.0
+                       "gpu_mrays_per_s_device": m_dev / dev_ms / 1e3, "device_rays": m_dev,
+                       "gpu_mrays_per_s_host_buffers": n / host_ms / 1e3, "host_buffers": "page-locked (ptb_host_alloc), chunk-pipelined",
+                       "hit_fraction": float(np.mean(p[:base] >= 0))}
+                if osc is not None:
+                    # CPU side on a bounded sample: the oracle's reference-faithful tree + leaf kernels
+                    ns = min(n, 1 << 18)
+                    t0 = time.perf_counter()
+                    t_ref, p_ref, cn = osc.intersect_batch(o[:ns], d[:ns], 0.0, 3.0e38, n_threads=os.cpu_count())
+                    dt = time.perf_counter() - t0
+                    row["cpu_mrays_per_s"] = ns / dt / 1e6
+                    row["cpu_sample_rays"] = ns
+                    row["cpu_threads"] = os.cpu_count()
+                    row["prim_agreement"] = float(np.mean(p[:ns] == p_ref))
+                    hit = (p[:ns] == p_ref) & (p_ref >= 0)
+                    row["t_rel_err_p99"] = float(np.quantile(np.abs(t[:ns][hit] - t_ref[hit]) / t_ref[hit], 0.99)) if hit.any() else 0.0
+                    if kind == "triangles":
+                        class _C:  # per-ray counts of the sample, in the shape roofline() reads
+                            rays, box_tests, sphere_tests, tri_tests = ns, cn.box_tests, cn.sphere_tests, cn.tri_tests
+                        key = {(1_000_000, False): "soup_1m_incoherent", (1_000_000, True): "soup_1m_coherent"}.get((m, coherent))
+                        row["roofline"] = roofline(m_dev / (dev_ms * 1e-3), _C, bytes_per_ray(key) if key else None)
+                else:
+                    row["cpu_note"] = "no CPU side: the reference tree over 10^7 triangles is not built in a sweep (tests/test_baseline_sizes.py checks this size against an Array_leaf scan and across device builders)"
                 log(json.dumps(row))
                 res.append(row)
+                del o, d, t, p
     return res
 
 
@@ -147,7 +231,13 @@ def main():
     nf = 100_000 if a.quick else a.mesh_faces
     doc["configs"].append(render_config(f"C3 synthetic ganesha mesh ({nf} faces) 1920x1080 256spp 8b",
                                         lambda w, h: P.synthetic_mesh_scene(nf, w, h), 1920, 1080, 32 if a.quick else 256, 8,
-                                        (320, 180, 16)))
+                                        (320, 180, 16), bkeys=("c3_1m_bounce0", "c3_1m_bounce1")))
+    if not a.quick:
+        doc["configs"].append(render_config("C3 synthetic ganesha mesh (10000000 faces) 1920x1080 256spp 8b",
+                                            lambda w, h: P.synthetic_mesh_scene(10_000_000 if w == 1920 else 1_000_000, w, h), 1920,
+                                            1080, 256, 8, (320, 180, 16), bkeys=("c3_10m_bounce0", "c3_10m_bounce1")))
+    doc["configs"].append(render_config("C2 as written: cornell geometry + emissive square + light sampling (extension), 1024x1024 256spp 16b",
+                                        lambda w, h: P.cornell_box_lit(w, h), 1024, 1024, 64 if a.quick else 256, 16, (256, 256, 16)))
     if not a.skip_sweep:
         doc["sweep"] = sweep(a.quick)
     print(json.dumps(doc))
