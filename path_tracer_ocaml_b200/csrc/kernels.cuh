@@ -184,7 +184,9 @@ __device__ __forceinline__ Quat<R> frame_from_normal(V3<R> n) {
 // lib.rs:160-166, is the same idea).
 // UNIT: the ray direction has unit length (every ray of the render pipeline: Camera.ray normalizes, world_ray rotates
 // unit vectors), so a = d.d = 1 drops out: three multiplies and two live registers less per test.
-template <bool UNIT>
+// TMIN0: t_min is 0, so "0 <= t <= tbest" is ONE unsigned comparison of the bit patterns (tbest is a non-negative
+// number: every negative or NaN t has a larger pattern than any such tbest).
+template <bool UNIT, bool TMIN0 = false>
 __device__ __forceinline__ bool sphere_test_f(Vec4<float> s, V3<float> o, V3<float> d, float a, float inv_a,
                                               float tmin, float &tbest) {
   const V3<float> f = {s.x - o.x, s.y - o.y, s.z - o.z};
@@ -195,7 +197,8 @@ __device__ __forceinline__ bool sphere_test_f(Vec4<float> s, V3<float> o, V3<flo
   const float q = bp + copysignf(r_sqrt_fast(UNIT ? disc : a * disc), bp);
   const float c = fmaf(f.x, f.x, fmaf(f.y, f.y, fmaf(f.z, f.z, -s.w)));
   const float t = (c > 0.0f) ? c * r_rcp(q) : (UNIT ? q : q * inv_a);
-  const bool ok = (t >= tmin) && (t <= tbest);  // `<=`: a later equal t wins (lib.rs:171-176)
+  // `<=`: a later equal t wins (lib.rs:171-176)
+  const bool ok = TMIN0 ? (__float_as_uint(t) <= __float_as_uint(tbest)) : ((t >= tmin) && (t <= tbest));
   tbest = ok ? t : tbest;
   return ok;
 }
@@ -510,16 +513,33 @@ struct Lane {
 template <class R, bool UNIT = false>
 __device__ __forceinline__ void lane_init(Lane<R> &L, V3<R> o, V3<R> d, R tmin, R tmax, unsigned sp0, int root = 0) {
   constexpr unsigned ROW = 4u * (unsigned)sizeof(R);
-  auto safe_rcp = [](R x) {
-    return (r_abs(x) < Lim<R>::tiny()) ? r_copysign(R(1) / Lim<R>::tiny(), x) : r_rcp(x);
-  };
-  L.o = o, L.d = d;
-  L.idir = {safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z)};
+  if constexpr (sizeof(R) == 4 && UNIT) {
+    // Render pipeline, float: plain reciprocals.  A zero (or denormal) direction component gives +-inf here and
+    // inf - inf = NaN in the slab arithmetic; min/max return their non-NaN operand, so such an axis simply drops out
+    // of the slab test — a conservative answer (the ray runs parallel to those planes; camera and scattered directions
+    // practically never have an exact zero), reached without the three compare-and-patch sequences a guarded
+    // reciprocal costs per refilled ray.  The near / far rows are chosen by the SIGN BIT, so that -0.0 (whose
+    // reciprocal is -inf) reads its planes in the order its reciprocal implies.  Caller-supplied rays
+    // (intersect_batch), where axis-parallel directions are common, keep the guarded form below.
+    L.idir = {r_rcp(d.x), r_rcp(d.y), r_rcp(d.z)};
+    L.onx = r2i(d.x) < 0 ? 3u * ROW : 0u;  // rows: lo.x lo.y lo.z hi.x hi.y hi.z
+    L.ony = r2i(d.y) < 0 ? 4u * ROW : ROW;
+    L.onz = r2i(d.z) < 0 ? 5u * ROW : 2u * ROW;
+  } else {
+    auto safe_rcp = [](R x) {
+      return (r_abs(x) < Lim<R>::tiny()) ? r_copysign(R(1) / Lim<R>::tiny(), x) : r_rcp(x);
+    };
+    L.idir = {safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z)};
+    L.onx = d.x >= R(0) ? 0u : 3u * ROW;  // rows: lo.x lo.y lo.z hi.x hi.y hi.z
+    L.ony = d.y >= R(0) ? ROW : 4u * ROW;
+    L.onz = d.z >= R(0) ? 2u * ROW : 5u * ROW;
+  }
   L.oid = {o.x * L.idir.x, o.y * L.idir.y, o.z * L.idir.z};
   if constexpr (sizeof(R) == 4) {
     L.ix2 = pack2(L.idir.x, L.idir.x), L.iy2 = pack2(L.idir.y, L.idir.y), L.iz2 = pack2(L.idir.z, L.idir.z);
     L.nox2 = pack2(-L.oid.x, -L.oid.x), L.noy2 = pack2(-L.oid.y, -L.oid.y), L.noz2 = pack2(-L.oid.z, -L.oid.z);
   }
+  L.o = o, L.d = d;
   if constexpr (!UNIT) {
     L.a = dot(d, d);
     L.inv_a = r_rcp(L.a);
@@ -527,9 +547,6 @@ __device__ __forceinline__ void lane_init(Lane<R> &L, V3<R> o, V3<R> d, R tmin, 
   L.tmin = tmin, L.tbest = tmax;
   L.best = -1, L.cur = root;
   L.sp = sp0;
-  L.onx = d.x >= R(0) ? 0u : 3u * ROW;  // rows: lo.x lo.y lo.z hi.x hi.y hi.z
-  L.ony = d.y >= R(0) ? ROW : 4u * ROW;
-  L.onz = d.z >= R(0) ? 2u * ROW : 5u * ROW;
 }
 
 // One traversal iteration of a warp = node phase, leaf phase, pop phase; each lane takes part in the phases
@@ -621,29 +638,37 @@ __device__ __forceinline__ void node_phase(Lane<R> &L, const SceneRef<R, SMEM> &
   }
 }
 
+// Sphere leaves of a tree staged in shared memory (float) are DIRECT: the block rewrites their child references to
+// -(shared address of the first record | count - 1), so a leaf visit starts with two logic instructions instead of
+// the unpacking of (first, count, type) and two address computations.  Triangle leaves keep the packed code.
+constexpr int DIRECT_LEAF_MIN = -(1 << 24);  // direct codes are > this (shared addresses are < 2^18), packed ones far below
 template <class R, bool SMEM, bool TMIN0, bool UNIT>
 __device__ __forceinline__ void leaf_phase(Lane<R> &L, const SceneRef<R, SMEM> &S) {
-  const unsigned code = ~(unsigned)L.cur;
-  const int first = (int)(code & 0x3FFFFFFu);
-  const int cnt = (int)((code >> 26) & 15u) + 1;
   const R tmin = TMIN0 ? R(0) : L.tmin;
-  if (((code >> 30) & 1u) == 0u) {
-    if constexpr (SMEM && sizeof(R) == 4) {
+  if constexpr (SMEM && sizeof(R) == 4) {
+    if (L.cur > DIRECT_LEAF_MIN) {
       // walk the leaf's records by shared-memory address; the hit is remembered as an address and turned into a
       // slot once per leaf (3 instructions of loop control per sphere instead of 6)
-      unsigned addr = S.s_spheres + (unsigned)first * 16u, hit = 0u;
-      const unsigned end = addr + (unsigned)cnt * 16u;
+      const unsigned x = (unsigned)(-L.cur);
+      unsigned addr = x & ~15u, hit = 0u;
+      const unsigned end = addr + 16u + (x & 15u) * 16u;
 #pragma unroll 1
       do {
-        const bool ok = sphere_test_f<UNIT>(lds_vec4(addr, float()), L.o, L.d, UNIT ? 1.0f : L.a, UNIT ? 1.0f : L.inv_a, tmin, L.tbest);
+        const bool ok = sphere_test_f<UNIT, TMIN0>(lds_vec4(addr, float()), L.o, L.d, UNIT ? 1.0f : L.a, UNIT ? 1.0f : L.inv_a, tmin, L.tbest);
         hit = ok ? addr : hit;
         addr += 16u;
       } while (addr < end);
       if (hit) L.best = (int)((hit - S.s_spheres) >> 4);
-    } else {
-#pragma unroll 1
-      for (int i = 0; i < cnt; ++i) sphere_test(S.sphere(first + i), L.o, L.d, L.a, L.inv_a, tmin, L.tbest, L.best, first + i);
+      L.cur = TRAV_POP;
+      return;
     }
+  }
+  const unsigned code = ~(unsigned)L.cur;
+  const int first = (int)(code & 0x3FFFFFFu);
+  const int cnt = (int)((code >> 26) & 15u) + 1;
+  if (((code >> 30) & 1u) == 0u) {
+#pragma unroll 1
+    for (int i = 0; i < cnt; ++i) sphere_test(S.sphere(first + i), L.o, L.d, L.a, L.inv_a, tmin, L.tbest, L.best, first + i);
   } else {
 #pragma unroll 1
     for (int i = 0; i < cnt; ++i)
@@ -893,7 +918,13 @@ __global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, SM
     Node4<R> *snodes = reinterpret_cast<Node4<R> *>(smem);
     for (unsigned i = tid; i < 4u * (unsigned)sc.n_nodes; i += nthreads) {
       const int c = snodes[i >> 2].child[i & 3u];
-      if (c >= 0) snodes[i >> 2].child[i & 3u] = (int)(smem_base + (unsigned)c * (unsigned)sizeof(Node4<R>));
+      if (c >= 0) {
+        snodes[i >> 2].child[i & 3u] = (int)(smem_base + (unsigned)c * (unsigned)sizeof(Node4<R>));
+      } else if (sizeof(R) == 4 && c != INT32_MIN) {  // (INT32_MIN = EMPTY_CHILD: an unused slot)
+        const unsigned code = ~(unsigned)c;
+        if (((code >> 30) & 1u) == 0u)  // sphere leaf -> direct (leaf_phase)
+          snodes[i >> 2].child[i & 3u] = -(int)((S.s_spheres + (code & 0x3FFFFFFu) * 16u) | ((code >> 26) & 15u));
+      }
     }
     __syncthreads();
   }
