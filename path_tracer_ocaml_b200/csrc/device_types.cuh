@@ -89,10 +89,11 @@ template <class R>
 struct Queue {
   Vec4<R> *base;
   int32_t *seg_count;
-  static __host__ __device__ __forceinline__ unsigned idx(unsigned e) { return e + ((e >> 7) << 8); }  // e/SEG*3*SEG + e%SEG
-  __host__ __device__ __forceinline__ Vec4<R> *A(unsigned e) const { return base + idx(e); }
-  __host__ __device__ __forceinline__ Vec4<R> *B(unsigned e) const { return base + idx(e) + SEG; }
-  __host__ __device__ __forceinline__ Vec4<R> *C(unsigned e) const { return base + idx(e) + 2 * SEG; }
+  // e/SEG*3*SEG + e%SEG = e + 2*SEG*(e/SEG), in 64 bits: a 512 Mi-path batch has 1.6 G entries in the joint hit queue
+  static __host__ __device__ __forceinline__ size_t idx(unsigned e) { return (size_t)e + (size_t)(e >> 7) * (2u * SEG); }
+  __host__ __device__ __forceinline__ Vec4<R> *A(unsigned e) const { return base + e + (size_t)(e >> 7) * (2u * SEG); }
+  __host__ __device__ __forceinline__ Vec4<R> *B(unsigned e) const { return A(e) + SEG; }
+  __host__ __device__ __forceinline__ Vec4<R> *C(unsigned e) const { return A(e) + 2 * SEG; }
 };
 static_assert(SEG == 128, "Queue::idx hard-codes SEG = 128");
 

@@ -624,18 +624,23 @@ __device__ __forceinline__ void node_phase(Lane<R> &L, const SceneRef<R, SMEM> &
   // is followed only if it starts before the best hit — the others are culled when they are popped
   L.cur = (sizeof(R) == 4 ? (t0 <= L.tbest) : (t0 < INF)) ? c0 : TRAV_POP;
   // (t0 == INF implies t1..t3 == INF: nothing is pushed)
-  if (t3 < INF && (!CHECK || L.sp < sp_limit)) {
+  // float path: a child is pushed only if it starts before the best hit — the same comparison instruction as the
+  // test against +inf, and it spares the store and the pop of every child the unclipped slab test let through
+  const R push_below = sizeof(R) == 4 ? L.tbest : INF;
+#define PTB_PUSHABLE(t) (sizeof(R) == 4 ? (t) <= push_below : (t) < push_below)
+  if (PTB_PUSHABLE(t3) && (!CHECK || L.sp < sp_limit)) {
     K.store(L.sp, c3, t3);
     L.sp += K.stride;
   }
-  if (t2 < INF && (!CHECK || L.sp < sp_limit)) {
+  if (PTB_PUSHABLE(t2) && (!CHECK || L.sp < sp_limit)) {
     K.store(L.sp, c2, t2);
     L.sp += K.stride;
   }
-  if (t1 < INF && (!CHECK || L.sp < sp_limit)) {
+  if (PTB_PUSHABLE(t1) && (!CHECK || L.sp < sp_limit)) {
     K.store(L.sp, c1, t1);
     L.sp += K.stride;
   }
+#undef PTB_PUSHABLE
 }
 
 // Sphere leaves of a tree staged in shared memory (float) are DIRECT: the block rewrites their child references to

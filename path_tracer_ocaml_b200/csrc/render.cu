@@ -464,7 +464,7 @@ static void launch_trace(const TraceLaunch &tl, cudaStream_t st, const DScene<R>
 // is halved until they fit in 60 % of the memory that is free.
 static size_t batch_capacity(size_t have /* capacity of the queues the device pool already holds */,
                              size_t vec4_bytes /* sizeof(Vec4<R>) of the pipeline that will run */) {
-  size_t nb = (size_t)1 << 28;
+  size_t nb = (size_t)1 << 29;
   if (const char *e = std::getenv("PTB_BATCH")) {
     long long v = std::atoll(e);
     if (v >= 1024) nb = (size_t)v;
@@ -476,7 +476,7 @@ static size_t batch_capacity(size_t have /* capacity of the queues the device po
     free_b += have * per_path;  // growing frees the old queues first
     while (nb > have && nb > ((size_t)1 << 20) && nb * per_path > free_b / 10 * 6) nb >>= 1;
   }
-  return std::max(nb, std::min(have, (size_t)1 << 28));
+  return std::max(nb, std::min(have, (size_t)1 << 29));
 }
 
 // The wavefront loop: raygen, then per bounce trace -> shade, batch after batch, all asynchronous on
