@@ -486,14 +486,17 @@ constexpr int TRAV_IDLE = INT32_MIN;
 constexpr int TRAV_DONE = INT32_MIN + 1;
 constexpr int TRAV_POP = INT32_MIN + 2;
 
+// compare-exchange of (t, child) pairs: the distances go through min / max (they do not wait for the comparison),
+// the child references through two selects
 #define PTB_CSWAP(ta, ca, tb, cb)   \
   {                                 \
-    bool sw_ = tb < ta;             \
-    R tt_ = sw_ ? ta : tb;          \
-    int cc_ = sw_ ? ca : cb;        \
-    ta = sw_ ? tb : ta;             \
+    const bool sw_ = tb < ta;       \
+    const R lo_ = r_min(ta, tb);    \
+    const R hi_ = r_max(ta, tb);    \
+    const int cc_ = sw_ ? ca : cb;  \
     ca = sw_ ? cb : ca;             \
-    tb = tt_;                       \
+    ta = lo_;                       \
+    tb = hi_;                       \
     cb = cc_;                       \
   }
 

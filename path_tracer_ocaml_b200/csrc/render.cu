@@ -421,7 +421,7 @@ static int trace_config(DeviceState *d, const DScene<R> &sc, size_t scene_bytes,
 static int refill_below() {
   static int v = -1;
   if (v < 0) {
-    v = 12;  // measured flat between 8 and 14, slower above (also for global-memory triangle scenes: 12..28 within 4 %)
+    v = 10;  // measured flat between 8 and 14, slower above (also for global-memory triangle scenes: 12..28 within 4 %)
     if (const char *e = std::getenv("PTB_REFILL")) v = std::min(32, std::max(1, std::atoi(e)));
   }
   return v;
