@@ -35,6 +35,22 @@ struct alignas(16) Node4 {
 static_assert(sizeof(Node4<float>) == 112, "Node4<float> must be 7 x 16 bytes");
 static_assert(sizeof(Node4<double>) == 208, "Node4<double> must be 13 x 16 bytes");
 
+// Scenes that stay in GLOBAL memory, float: records sized for 256-bit loads.  The traversal of such a scene is bound
+// by the L1 data pipe — one wavefront per lane per load instruction, whatever its width, because every lane reads its
+// own node — so a node is read with 3 x 32 B + 16 B instead of 7 x 16 B and a triangle with 32 B + 4 B instead of
+// 3 x 16 B.  A node holds, per axis, the low planes of its four children and then the high ones; near and far are
+// told apart by min / max of the two plane distances (no address selection by the direction's sign).  An unused
+// child slot has NaN planes: its far distance is NaN and the (unordered) miss test rejects it.
+struct alignas(128) NodeG {
+  float pl[3][8];
+  int32_t child[4];
+  int32_t pad[4];
+};
+struct alignas(64) TriG {
+  float v[16];  // v0, e1, e2 (9 floats); the rest is padding
+};
+static_assert(sizeof(NodeG) == 128 && sizeof(TriG) == 64, "256-bit load records");
+
 struct alignas(16) DMat {
   int32_t kind;
   int32_t tex;
@@ -56,6 +72,9 @@ struct DScene {
   const Node4<R> *nodes;
   const Vec4<R> *spheres;  // (cx, cy, cz, r) per slot
   const Vec4<R> *tris;     // 3 per slot: (v0,_), (e1,_), (e2,_)
+  const NodeG *nodes_g;    // float scenes in global memory: the same tree and triangles as 256-bit load records
+  const TriG *tris_g;
+  const Vec4<R> *spheres_g;  // (cx, cy, cz, r^2), padded by 8 records
   const int32_t *sphere_id, *tri_id;    // slot -> caller index
   const int32_t *sphere_mat, *tri_mat;  // slot -> material row
   const uint8_t *prim_kind;             // slot -> material kind, spheres then triangles, padded to 16 B

@@ -434,12 +434,25 @@ __device__ __forceinline__ Vec4<double> ldg_vec4(const Vec4<double> *p) {
   return {a.x, a.y, b.x, b.y};
 }
 
+// 256-bit read-only global load (sm_100: LDG.E.256), 32-byte aligned
+struct F8 {
+  float v[8];
+};
+__device__ __forceinline__ F8 ldg256(const void *p) {
+  F8 r;
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+               : "l"(p));
+  return r;
+}
+
 // where the scene lives for this launch: shared memory (staged by the block) or global memory
 template <class R, bool SMEM>
 struct SceneRef {
   unsigned s_nodes, s_spheres, s_tris, s_kinds;  // shared-window byte addresses (SMEM)
   const char *g_nodes;
   const Vec4<R> *g_spheres, *g_tris;
+  const char *g_nodes_g, *g_tris_g, *g_sph_g;  // float, global memory: NodeG / TriG records, spheres as (c, r^2)
   const uint8_t *g_kinds;
   static constexpr unsigned ROW = 4u * (unsigned)sizeof(R);  // one SoA row of a node: 4 children of one plane
   // material kind of a primitive; `best` = slot | type << 30; table = spheres then triangles
@@ -560,19 +573,23 @@ __device__ __forceinline__ void lane_init(Lane<R> &L, V3<R> o, V3<R> d, R tmin, 
 // pushed as they come — every pushed child is still visited unless its t_near exceeds the best hit, so the
 // closest hit is unchanged (measured: +2 % node visits, -10 instructions per node).  CHECK: stack overflow
 // guard (only when the tree's worst case exceeds the capacity).
+template <class R, bool FULLSORT, bool CHECK, class STACK>
+__device__ __forceinline__ void node_finish(Lane<R> &L, STACK &K, unsigned sp_limit, R tnx, R tny, R tnz, R tnw, int4 ch);
+
 template <class R, bool SMEM, bool TMIN0, bool FULLSORT, bool CHECK>
 __device__ __forceinline__ void node_phase(Lane<R> &L, const SceneRef<R, SMEM> &S, Stack<R, !SMEM> &K, unsigned sp_limit) {
   constexpr unsigned ROW = 4u * (unsigned)sizeof(R);
-  const Vec4<R> bnx = S.nrow(L.cur, L.onx), bny = S.nrow(L.cur, L.ony), bnz = S.nrow(L.cur, L.onz);
-  const Vec4<R> bfx = S.nrow(L.cur, 3u * ROW - L.onx), bfy = S.nrow(L.cur, 5u * ROW - L.ony),
-                bfz = S.nrow(L.cur, 7u * ROW - L.onz);
-  const int4 ch = S.children(L.cur);
   const R INF = Lim<R>::inf();
   const R tmin = TMIN0 ? R(0) : L.tmin;
   // float boxes are padded outward on the host (render.cu box_lo/box_hi), which covers the rounding of the
   // plane distances; the unpadded double boxes get a relative slack on the far side instead
   R tnx, tny, tnz, tnw;
+  int4 ch;
   if constexpr (sizeof(R) == 4) {
+    const Vec4<R> bnx = S.nrow(L.cur, L.onx), bny = S.nrow(L.cur, L.ony), bnz = S.nrow(L.cur, L.onz);
+    const Vec4<R> bfx = S.nrow(L.cur, 3u * ROW - L.onx), bfy = S.nrow(L.cur, 5u * ROW - L.ony),
+                  bfz = S.nrow(L.cur, 7u * ROW - L.onz);
+    ch = S.children(L.cur);
     // 12 FFMA2 instead of 24 FFMA: children (x,y) and (z,w) of a row are the register pairs of its LDS.128
 #define PTB_ROW(row, i2, no2, a, b, c, d)                            \
   float a, b, c, d;                                                  \
@@ -599,6 +616,10 @@ __device__ __forceinline__ void node_phase(Lane<R> &L, const SceneRef<R, SMEM> &
     PTB_SLAB(w, 3)
 #undef PTB_SLAB
   } else {
+    const Vec4<R> bnx = S.nrow(L.cur, L.onx), bny = S.nrow(L.cur, L.ony), bnz = S.nrow(L.cur, L.onz);
+    const Vec4<R> bfx = S.nrow(L.cur, 3u * ROW - L.onx), bfy = S.nrow(L.cur, 5u * ROW - L.ony),
+                  bfz = S.nrow(L.cur, 7u * ROW - L.onz);
+    ch = S.children(L.cur);
 #define PTB_SLAB(k)                                                                                       \
   tn##k = r_max(r_max(r_fma(bnx.k, L.idir.x, -L.oid.x), r_fma(bny.k, L.idir.y, -L.oid.y)),                \
                 r_max(r_fma(bnz.k, L.idir.z, -L.oid.z), tmin));                                           \
@@ -614,6 +635,13 @@ __device__ __forceinline__ void node_phase(Lane<R> &L, const SceneRef<R, SMEM> &
     PTB_SLAB(w)
 #undef PTB_SLAB
   }
+  node_finish<R, FULLSORT, CHECK>(L, K, sp_limit, tnx, tny, tnz, tnw, ch);
+}
+
+// second half of a node visit: order the children that were hit, follow the nearest, push the others
+template <class R, bool FULLSORT, bool CHECK, class STACK>
+__device__ __forceinline__ void node_finish(Lane<R> &L, STACK &K, unsigned sp_limit, R tnx, R tny, R tnz, R tnw, int4 ch) {
+  const R INF = Lim<R>::inf();
   int c0 = ch.x, c1 = ch.y, c2 = ch.z, c3 = ch.w;
   R t0 = tnx, t1 = tny, t2 = tnz, t3 = tnw;
   PTB_CSWAP(t0, c0, t1, c1)
@@ -676,7 +704,8 @@ __device__ __forceinline__ void leaf_phase(Lane<R> &L, const SceneRef<R, SMEM> &
   const int cnt = (int)((code >> 26) & 15u) + 1;
   if (((code >> 30) & 1u) == 0u) {
 #pragma unroll 1
-    for (int i = 0; i < cnt; ++i) sphere_test(S.sphere(first + i), L.o, L.d, L.a, L.inv_a, tmin, L.tbest, L.best, first + i);
+    for (int i = 0; i < cnt; ++i)
+      sphere_test(S.sphere(first + i), L.o, L.d, UNIT ? R(1) : L.a, UNIT ? R(1) : L.inv_a, tmin, L.tbest, L.best, first + i);
   } else {
 #pragma unroll 1
     for (int i = 0; i < cnt; ++i)
@@ -695,6 +724,86 @@ __device__ __forceinline__ void pop_phase(Lane<R> &L, const Stack<R, LOCAL> &K) 
     L.sp -= K.stride;
     K.load(L.sp, L.cur, t);
   } while (t > L.tbest);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Global-memory scenes, float: ONE traversal step per lane and warp iteration, fed by ONE fetch.
+// Traversal of a scene that does not fit shared memory is bound by memory latency (ncu: 9 of 10 warp cycles wait on
+// a load), so what counts is how many dependent round trips a ray needs and how many lanes have a load in flight.
+// Every traversing lane therefore reads 112 bytes at ITS address first — a node (NodeG), the next two triangles of
+// its leaf (2 x TriG), or the (up to four) spheres of its leaf — with the same four load instructions, and only
+// then the warp branches into the node step and the primitive tests: one round trip per iteration for the whole
+// warp, where separate node and leaf phases (and a leaf loop that loads one triangle at a time) paid up to five.
+// A triangle leaf with more than two triangles stays the lane's `cur`, advanced by two, for the next iteration.
+// ---------------------------------------------------------------------------------------------
+template <bool TMIN0, bool UNIT, bool CHECK>
+__device__ __forceinline__ void fused_step_g(Lane<float> &L, const SceneRef<float, false> &S, Stack<float, true> &K,
+                                             unsigned sp_limit) {
+  const int cur = L.cur;
+  if (cur <= TRAV_POP) return;  // (idle, finished)
+  const unsigned code = ~(unsigned)cur;
+  const bool is_tri = ((code >> 30) & 1u) != 0u;
+  const unsigned first = code & 0x3FFFFFFu;
+  const char *p = cur >= 0 ? S.g_nodes_g + (size_t)(unsigned)cur * sizeof(NodeG)
+                           : (is_tri ? S.g_tris_g + (size_t)first * sizeof(TriG)
+                                     : S.g_sph_g + (size_t)(first & ~1u) * sizeof(Vec4<float>));
+  // (Loading the second half of the record only where it is needed — nodes, a second triangle, a fifth sphere —
+  // was measured: 3 % slower on the soup, 4 % on the C3 mesh; profiles/README.md round 2.)
+  const unsigned cnt = ((code >> 26) & 15u) + 1u;  // (leaves)
+  const F8 X = ldg256(p), Y = ldg256(p + 32), Z = ldg256(p + 64);
+  const int4 W = __ldg(reinterpret_cast<const int4 *>(p + 96));
+  const float tmin = TMIN0 ? 0.0f : L.tmin;
+  if (cur >= 0) {
+    float tnx, tny, tnz, tnw;
+#define PTB_AXIS(P, i2, no2, a)                                                   \
+  float a##l0, a##l1, a##l2, a##l3, a##h0, a##h1, a##h2, a##h3;                    \
+  unpack2(ffma2(pack2(P.v[0], P.v[1]), L.i2, L.no2), a##l0, a##l1);                \
+  unpack2(ffma2(pack2(P.v[2], P.v[3]), L.i2, L.no2), a##l2, a##l3);                \
+  unpack2(ffma2(pack2(P.v[4], P.v[5]), L.i2, L.no2), a##h0, a##h1);                \
+  unpack2(ffma2(pack2(P.v[6], P.v[7]), L.i2, L.no2), a##h2, a##h3);
+    PTB_AXIS(X, ix2, nox2, x)
+    PTB_AXIS(Y, iy2, noy2, y)
+    PTB_AXIS(Z, iz2, noz2, z)
+#undef PTB_AXIS
+    // near / far by min / max of the two plane distances; an unused slot (NaN planes) has a NaN far distance and
+    // fails the unordered comparison
+#define PTB_SLAB(k, i)                                                                                            \
+  tn##k = fmaxf(fmaxf(fminf(xl##i, xh##i), fminf(yl##i, yh##i)), fmaxf(fminf(zl##i, zh##i), tmin));                \
+  {                                                                                                               \
+    const float tf_ = fminf(fminf(fmaxf(xl##i, xh##i), fmaxf(yl##i, yh##i)), fmaxf(zl##i, zh##i));                 \
+    asm("{\n.reg .pred p;\nsetp.gtu.f32 p, %0, %1;\n@p add.f32 %0, %0, 0f7F800000;\n}" : "+f"(tn##k) : "f"(tf_)); \
+  }
+    PTB_SLAB(x, 0)
+    PTB_SLAB(y, 1)
+    PTB_SLAB(z, 2)
+    PTB_SLAB(w, 3)
+#undef PTB_SLAB
+    node_finish<float, false, CHECK>(L, K, sp_limit, tnx, tny, tnz, tnw, W);
+    return;
+  }
+  if (is_tri) {
+    tri_test<float>(Vec4<float>{X.v[0], X.v[1], X.v[2], 0.f}, Vec4<float>{X.v[3], X.v[4], X.v[5], 0.f},
+                    Vec4<float>{X.v[6], X.v[7], Y.v[0], 0.f}, L.o, L.d, tmin, L.tbest, L.best, (int)(first | (1u << 30)));
+    if (cnt > 1u)
+      tri_test<float>(Vec4<float>{Z.v[0], Z.v[1], Z.v[2], 0.f}, Vec4<float>{Z.v[3], Z.v[4], Z.v[5], 0.f},
+                      Vec4<float>{Z.v[6], Z.v[7], __int_as_float(W.x), 0.f}, L.o, L.d, tmin, L.tbest, L.best,
+                      (int)((first + 1u) | (1u << 30)));
+    L.cur = cnt <= 2u ? TRAV_POP : (int)~(code + 2u - (2u << 26));  // (first += 2, count -= 2)
+  } else {
+    // records (first & ~1) .. +6 are in; the leaf starts at the first or the second of them
+    const bool odd = (first & 1u) != 0u;
+    const float a = UNIT ? 1.0f : L.a, inv_a = UNIT ? 1.0f : L.inv_a;
+#define PTB_SPH(k, e0, e1, e2, e3, o0, o1, o2, o3)                                                              \
+  if (cnt > k)                                                                                                    \
+    sphere_test(odd ? Vec4<float>{o0, o1, o2, o3} : Vec4<float>{e0, e1, e2, e3}, L.o, L.d, a, inv_a, tmin, L.tbest, \
+                L.best, (int)(first + k));
+    PTB_SPH(0u, X.v[0], X.v[1], X.v[2], X.v[3], X.v[4], X.v[5], X.v[6], X.v[7])
+    PTB_SPH(1u, X.v[4], X.v[5], X.v[6], X.v[7], Y.v[0], Y.v[1], Y.v[2], Y.v[3])
+    PTB_SPH(2u, Y.v[0], Y.v[1], Y.v[2], Y.v[3], Y.v[4], Y.v[5], Y.v[6], Y.v[7])
+    PTB_SPH(3u, Y.v[4], Y.v[5], Y.v[6], Y.v[7], Z.v[0], Z.v[1], Z.v[2], Z.v[3])
+#undef PTB_SPH
+    L.cur = cnt <= 4u ? TRAV_POP : (int)~(code + 4u - (4u << 26));
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -896,6 +1005,8 @@ __global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, SM
   const unsigned smem_base = (unsigned)__cvta_generic_to_shared(smem);
   SceneRef<R, SMEM> S;
   S.g_nodes = reinterpret_cast<const char *>(sc.nodes), S.g_spheres = sc.spheres, S.g_tris = sc.tris;
+  S.g_nodes_g = reinterpret_cast<const char *>(sc.nodes_g), S.g_tris_g = reinterpret_cast<const char *>(sc.tris_g);
+  S.g_sph_g = reinterpret_cast<const char *>(sc.spheres_g);
   S.g_kinds = sc.prim_kind;
   unsigned scene_bytes = 0;
   if (SMEM) {
@@ -1214,6 +1325,13 @@ __global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, SM
     unsigned act = active;
     int keep_r = keep;
     asm volatile("" : "+r"(keep_r));  // loop-invariant: keep it in a register instead of re-deriving it
+    if constexpr (!SMEM && sizeof(R) == 4) {
+      do {
+        fused_step_g<MODE == 0, UNIT, true>(L, S, K, sp_limit);
+        if (L.cur == TRAV_POP) pop_phase<R, true>(L, K);
+        act = __ballot_sync(0xffffffffu, L.cur > TRAV_DONE);
+      } while (__popc(act) >= keep_r);
+    } else
     do {
       if (L.cur >= 0) node_phase<R, SMEM, MODE == 0, sizeof(R) == 8, !SMEM>(L, S, K, sp_limit);
       const bool at_leaf = (unsigned)(L.cur - (TRAV_POP + 1)) < (unsigned)(0 - (TRAV_POP + 1));  // TRAV_POP < cur < 0
@@ -1635,6 +1753,38 @@ struct PeerPtrs {
   const float *src[8];
   int n;
 };
+// Commit of a float scene that stays in global memory: the tree and the triangles once more as NodeG / TriG records.
+__global__ void __launch_bounds__(256) k_make_g_layout(const Node4<float> *__restrict__ nodes, int n_nodes,
+                                                       const Vec4<float> *__restrict__ tris, int n_tris,
+                                                       const Vec4<float> *__restrict__ spheres, int n_spheres,
+                                                       NodeG *__restrict__ ng, TriG *__restrict__ tg,
+                                                       Vec4<float> *__restrict__ sg) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_spheres + 8) {  // (c, r^2); the 8 records of padding keep the 112-byte fetch of the last leaf inside the array
+    Vec4<float> v = {0.f, 0.f, 0.f, 0.f};
+    if (i < n_spheres) v = spheres[i], v.w *= v.w;
+    sg[i] = v;
+  }
+  if (i < n_nodes) {
+    const Node4<float> n = nodes[i];
+    NodeG g;
+    for (int k = 0; k < 4; ++k) {
+      const bool unused = n.child[k] == INT32_MIN;  // EMPTY_CHILD
+      for (int a = 0; a < 3; ++a) g.pl[a][k] = unused ? NAN : n.lo[a][k], g.pl[a][4 + k] = unused ? NAN : n.hi[a][k];
+      g.child[k] = n.child[k], g.pad[k] = 0;
+    }
+    ng[i] = g;
+  }
+  if (i < n_tris) {
+    const Vec4<float> v0 = tris[3 * (size_t)i], e1 = tris[3 * (size_t)i + 1], e2 = tris[3 * (size_t)i + 2];
+    TriG t;
+    t.v[0] = v0.x, t.v[1] = v0.y, t.v[2] = v0.z, t.v[3] = e1.x, t.v[4] = e1.y, t.v[5] = e1.z;
+    t.v[6] = e2.x, t.v[7] = e2.y, t.v[8] = e2.z;
+    for (int k = 9; k < 16; ++k) t.v[k] = 0.f;
+    tg[i] = t;
+  }
+}
+
 __global__ void __launch_bounds__(256) k_reduce_peers(float *__restrict__ dst, PeerPtrs pp, size_t n) {
   const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;  // grid covers ceil(n / 4) threads
   if (i >= n) return;
