@@ -96,6 +96,12 @@ typedef struct ptb_params {
   int32_t tile_rank, tile_world;
   int32_t flags;
   int32_t device;            /* CUDA device ordinal */
+  /* pass range: this call renders the sample passes [pass_first, pass_first + pass_count) of the
+   * samples_per_pixel passes of integrator.ml:95 (`for pass = 0 to spp - 1`); the R2 offsets stay those of the
+   * full render (pixel + pass * spp), so consecutive ranges add up to exactly the full render's samples.
+   * {0, 0} = all passes.  ptb_render / ptb_render_multi normalise their image by the passes of the call (a
+   * progressive preview); ptb_render_device only adds sums. */
+  int32_t pass_first, pass_count;
 } ptb_params;
 
 typedef struct ptb_stats {

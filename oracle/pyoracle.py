@@ -27,7 +27,8 @@ class Params(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("samples_per_pixel", C.c_int32),
                 ("max_bounces", C.c_int32), ("lower_left_x", C.c_double), ("lower_left_y", C.c_double),
                 ("view_x", C.c_double), ("view_y", C.c_double), ("tile_rank", C.c_int32),
-                ("tile_world", C.c_int32), ("flags", C.c_int32), ("device", C.c_int32)]
+                ("tile_world", C.c_int32), ("flags", C.c_int32), ("device", C.c_int32),
+                ("pass_first", C.c_int32), ("pass_count", C.c_int32)]  # (the oracle renders whole frames: ignored)
 
 
 class Counters(C.Structure):

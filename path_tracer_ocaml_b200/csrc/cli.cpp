@@ -20,6 +20,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <atomic>
 #include <string>
 #include <thread>
@@ -32,6 +33,7 @@ namespace {
 
 struct Args {  // Render_command.Args.t (render_command.ml:6-14) + what the port adds
   int width = 0, height = 0, samples_per_pixel = 1, max_bounces = 8, device = 0, gpus = 1;
+  int preview_every = 0;  // > 0: render in batches of this many sample passes and rewrite the output after each
   std::string output = "output.png";
   bool no_progress = false, no_simd = false, f64 = false;
   std::string ply, background = "white";
@@ -140,6 +142,7 @@ Args parse(int argc, char **argv, int first) {
     else if (s == "--ganesha-ply" || s == "-ganesha-ply") a.ply = need();
     else if (s == "--synthetic-faces") a.synthetic_faces = std::atoll(need().c_str());
     else if (s == "--background") a.background = need();
+    else if (s == "--preview-every") a.preview_every = std::atoi(need().c_str());
     else die("unknown option '" + s + "'");
   }
   if (!have_dim) die("required option --dimension is missing");  // Arg.required (render_command.ml:21-25)
@@ -231,32 +234,58 @@ int main(int argc, char **argv) {
       }
       if (shown != ~0ull) std::fprintf(stderr, "\rRendering [########################################] 100%%\n");
     });
+  // Bimage_unix.Stb.write of an f64 image: 8-bit, truncating (pinned by the sky rows of the golden PNG,
+  // tests/golden/shirley_png_facts.json), clamped to [0, 255]
+  auto write_image = [&](const std::vector<double> &img) {
+    std::vector<unsigned char> rgb(img.size());
+    for (size_t i = 0; i < img.size(); ++i) {
+      double v = img[i] * 255.0;
+      rgb[i] = (unsigned char)(v < 0 ? 0 : v > 255 ? 255 : (int)v);
+    }
+    bool ok;
+    if (a.output.size() > 4 && a.output.substr(a.output.size() - 4) == ".ppm") {
+      FILE *f = std::fopen(a.output.c_str(), "wb");
+      ok = f != nullptr;
+      if (ok) {
+        std::fprintf(f, "P6\n%d %d\n255\n", a.width, a.height);
+        std::fwrite(rgb.data(), 1, rgb.size(), f);
+        ok = std::fclose(f) == 0;
+      }
+    } else {
+      ok = write_png(a.output, rgb, a.width, a.height);
+    }
+    if (!ok) die("cannot write " + a.output);
+  };
   auto t0 = clk::now();
-  int rrc = a.gpus > 1 ? ptb_render_multi(sc, &p, a.gpus, image.data(), &st) : ptb_render(sc, &p, image.data(), &st);
+  int rrc = 0;
+  if (a.preview_every > 0 && a.preview_every < a.samples_per_pixel) {
+    // Progressive output (what the reference's photon-map binary does per iteration, progressive_photon_map.ml:447-449):
+    // batches of sample passes (ptb_params.pass_first / pass_count), the filtered sums added up on the host, the
+    // output file rewritten with the image of the passes finished so far.  Same samples as the one-call render.
+    std::vector<double> acc(image.size(), 0.0), part(image.size());
+    ptb_stats total;
+    std::memset(&total, 0, sizeof total);
+    for (int first_pass = 0; first_pass < a.samples_per_pixel && rrc == 0; first_pass += a.preview_every) {
+      ptb_params q = p;
+      q.pass_first = first_pass, q.pass_count = std::min(a.preview_every, a.samples_per_pixel - first_pass);
+      q.flags |= PTB_FLAG_RAW_SUMS;
+      rrc = a.gpus > 1 ? ptb_render_multi(sc, &q, a.gpus, part.data(), &st) : ptb_render(sc, &q, part.data(), &st);
+      if (rrc) break;
+      total.paths += st.paths, total.rays += st.rays, total.kernel_launches += st.kernel_launches, total.ms_device += st.ms_device;
+      const double inv = 1.0 / (double)(first_pass + q.pass_count);
+      for (size_t i = 0; i < acc.size(); ++i) acc[i] += part[i], image[i] = std::sqrt(acc[i] * inv);  // integrator.ml:152-154
+      write_image(image);
+      if (!a.no_progress) std::fprintf(stderr, "\rpreview: %d of %d passes written to %s\n", first_pass + q.pass_count, a.samples_per_pixel, a.output.c_str());
+    }
+    st = total;
+  } else {
+    rrc = a.gpus > 1 ? ptb_render_multi(sc, &p, a.gpus, image.data(), &st) : ptb_render(sc, &p, image.data(), &st);
+  }
   const double ms = std::chrono::duration<double, std::milli>(clk::now() - t0).count();
   rendering.store(false);
   if (bar.joinable()) bar.join();
   check(rrc, "render");
-  // Bimage_unix.Stb.write of an f64 image: 8-bit, truncating (pinned by the sky rows of the golden PNG,
-  // tests/golden/shirley_png_facts.json), clamped to [0, 255]
-  std::vector<unsigned char> rgb(image.size());
-  for (size_t i = 0; i < image.size(); ++i) {
-    double v = image[i] * 255.0;
-    rgb[i] = (unsigned char)(v < 0 ? 0 : v > 255 ? 255 : (int)v);
-  }
-  bool ok;
-  if (a.output.size() > 4 && a.output.substr(a.output.size() - 4) == ".ppm") {
-    FILE *f = std::fopen(a.output.c_str(), "wb");
-    ok = f != nullptr;
-    if (ok) {
-      std::fprintf(f, "P6\n%d %d\n255\n", a.width, a.height);
-      std::fwrite(rgb.data(), 1, rgb.size(), f);
-      ok = std::fclose(f) == 0;
-    }
-  } else {
-    ok = write_png(a.output, rgb, a.width, a.height);
-  }
-  if (!ok) die("cannot write " + a.output);
+  if (!(a.preview_every > 0 && a.preview_every < a.samples_per_pixel)) write_image(image);
   std::printf("rendered in: %.3f ms\n", ms);  // render_command.ml:108
   std::printf("device: %.3f ms, %.1f Mpaths/s, %.1f Mrays/s, %llu kernel launches\n", st.ms_device,
               (double)st.paths / st.ms_device / 1e3, (double)st.rays / st.ms_device / 1e3,

@@ -320,6 +320,9 @@ static int ensure_pixel_list(DevicePool *d, int W, int H, int rank, int world) {
   return PTB_OK;
 }
 
+// passes rendered by a call (ptb_params.pass_first / pass_count; {0, 0} = all)
+static int passes_of(const ptb_params &p) { return p.pass_count > 0 ? p.pass_count : p.samples_per_pixel - p.pass_first; }
+
 static int fill_render_const(const ptb_params &p, int npix, RenderConst *rc) {
   if (p.width <= 0 || p.height <= 0 || p.samples_per_pixel <= 0)
     return fail(PTB_E_INVALID, "render: width, height and samples_per_pixel must be positive");
@@ -327,6 +330,9 @@ static int fill_render_const(const ptb_params &p, int npix, RenderConst *rc) {
     return fail(PTB_E_INVALID, "render: max_bounces must be in [0, 64]");
   if ((long long)p.width * p.height + (long long)p.samples_per_pixel * p.samples_per_pixel >= (1LL << 31))
     return fail(PTB_E_INVALID, "render: sample offset would overflow int32");
+  if (p.pass_first < 0 || p.pass_count < 0 || p.pass_first >= p.samples_per_pixel ||
+      (long long)p.pass_first + p.pass_count > p.samples_per_pixel)
+    return fail(PTB_E_INVALID, "render: pass range outside [0, samples_per_pixel)");
   std::memset(rc, 0, sizeof *rc);
   rc->W = p.width, rc->H = p.height, rc->spp = p.samples_per_pixel, rc->max_bounces = p.max_bounces;
   rc->npix = npix;
@@ -514,7 +520,8 @@ static int render_impl(ptb_scene *s, const ptb_params &p, R *d_sums, cudaStream_
   if ((rc = ensure_pixel_list(pl, p.width, p.height, p.tile_rank, world))) return rc;
   RenderConst rcst;
   if ((rc = fill_render_const(p, pl->npix, &rcst))) return rc;
-  const long long total = (long long)pl->npix * p.samples_per_pixel;
+  // samples [base, base + total) of the pass-major enumeration of this rank's pixels
+  const long long base = (long long)pl->npix * p.pass_first, total = (long long)pl->npix * passes_of(p);
   const size_t NB = std::min<size_t>(batch_capacity(pl->work<R>().cap, sizeof(Vec4<R>)), (size_t)std::max<long long>(total, 1));
   if ((rc = ensure_work<R>(pl, NB))) return rc;
   Work<R> &w = pl->work<R>();
@@ -574,7 +581,7 @@ static int render_impl(ptb_scene *s, const ptb_params &p, R *d_sums, cudaStream_
   for (long long first = 0; first < total; first += (long long)NB) {
     const unsigned n = (unsigned)std::min<long long>((long long)NB, total - first);
     k_batch_ctl<<<1, 128, 0, st>>>(ctl, n, p.max_bounces, pl->progress_dev, (unsigned long long)first);
-    const int pass0 = (int)(first / pl->npix), i0 = (int)(first % pl->npix);
+    const int pass0 = (int)((base + first) / pl->npix), i0 = (int)((base + first) % pl->npix);
     const GenConst gen = make_gen(rcst, pl->pixel_list, pass0, i0);  // bounce 0 generates its own camera rays
     launches += 1;
     for (int b = 0; b < p.max_bounces; ++b) {
@@ -670,7 +677,7 @@ static int render_host_impl(ptb_scene *s, const ptb_params &p, double *image, pt
   double *d_img = (double *)pl->img_buf;
   CK(cudaMemsetAsync(d_sums, 0, n3 * sizeof(R), 0));
   int rc = render_impl<R>(s, p, d_sums, 0, stats);
-  if (!rc) rc = resolve_impl<R, double>(d_sums, d_img, p.width, p.height, p.samples_per_pixel, p.flags, 0);
+  if (!rc) rc = resolve_impl<R, double>(d_sums, d_img, p.width, p.height, passes_of(p), p.flags, 0);
   if (!rc) {
     auto t0 = clk::now();
     cudaError_t e = cudaMemcpy(image, d_img, n3 * sizeof(double), cudaMemcpyDeviceToHost);
@@ -1190,7 +1197,7 @@ int ptb_render_multi(ptb_scene *s, const ptb_params *p, int32_t n_devices, doubl
     CK(cudaMalloc(&pl0->img_buf, n3 * sizeof(double)));
     pl0->img_cap = n3 * sizeof(double);
   }
-  rc = resolve_impl<float, double>(sums[0], (double *)pl0->img_buf, p->width, p->height, p->samples_per_pixel, p->flags, 0);
+  rc = resolve_impl<float, double>(sums[0], (double *)pl0->img_buf, p->width, p->height, passes_of(*p), p->flags, 0);
   if (rc) return rc;
   CK(cudaMemcpy(image, pl0->img_buf, n3 * sizeof(double), cudaMemcpyDeviceToHost));
   if (stats) {

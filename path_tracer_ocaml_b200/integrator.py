@@ -42,17 +42,39 @@ class Integrator:
     def create(cls, **kw):
         return cls(**kw)
 
-    def _p(self, flags):
+    def _p(self, flags, passes=None):
         p = capi.Params.from_buffer_copy(self.params)
         p.flags = flags
+        if passes is not None:
+            p.pass_first, p.pass_count = passes
         return p
 
     # Integrator.render with a HOST image (float64, 3*W*H, Bimage layout) — copies included.
-    def render(self, flags=0, image=None):
-        p = self._p(flags)
+    # passes = (first, count): only those sample passes, image normalised by `count` (ptb_params.pass_first/pass_count)
+    def render(self, flags=0, image=None, passes=None):
+        p = self._p(flags, passes)
         if image is None:
             image = np.empty((p.height, p.width, 3), dtype=np.float64)
         check(lib().ptb_render(self.scene.h, C.byref(p), dptr(image), C.byref(self.stats)))
+        return image
+
+    def render_progressive(self, every, on_preview=None, flags=0):
+        """The render in batches of `every` sample passes.  After each batch `on_preview(image, passes_done)` gets the
+        image of the passes finished so far (filtered, gamma applied) — the progressive output of the reference's
+        photon-map binary (progressive_photon_map.ml:447-449, the PNG rewritten per iteration) offered for the path
+        tracer.  Returns the final image: the same samples as render(), combined in float64 on the host."""
+        spp = self.params.samples_per_pixel
+        acc = np.zeros((self.params.height, self.params.width, 3), dtype=np.float64)
+        rays = paths = 0
+        for first in range(0, spp, every):
+            count = min(every, spp - first)
+            acc += self.render(flags=flags | capi.PTB_FLAG_RAW_SUMS, passes=(first, count))  # filtered sums of the batch
+            rays, paths = rays + self.stats.rays, paths + self.stats.paths
+            raw = flags & (capi.PTB_FLAG_RAW_SUMS | capi.PTB_FLAG_NO_FILTER)
+            image = acc.copy() if raw else np.sqrt(acc / (first + count))  # integrator.ml:152-154
+            if on_preview is not None:
+                on_preview(image, first + count)
+        self.stats.rays, self.stats.paths = rays, paths
         return image
 
     # single-process multi-GPU: tiles dealt to n_devices GPUs, peer-memory reduce on device 0
@@ -66,10 +88,10 @@ class Integrator:
         return image
 
     # device-resident path: adds this rank's per-pixel sums into a torch float32 CUDA tensor
-    def render_device(self, sums, flags=0, stream=None):
+    def render_device(self, sums, flags=0, stream=None, passes=None):
         import torch
         assert sums.is_cuda and sums.dtype == torch.float32 and sums.is_contiguous()
-        p = self._p(flags)
+        p = self._p(flags, passes)
         st = torch.cuda.current_stream(sums.device) if stream is None else stream
         check(lib().ptb_render_device(self.scene.h, C.byref(p), C.c_void_p(sums.data_ptr()),
                                       C.c_void_p(st.cuda_stream), C.byref(self.stats)))

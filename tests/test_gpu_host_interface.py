@@ -132,3 +132,51 @@ def test_single_process_multi_gpu_odd_frame_sizes():
         ref = P.Integrator(P.shirley_spheres(W, H), W, H, 8, 8).render()
         img = P.Integrator(P.shirley_spheres(W, H), W, H, 8, 8).render_multi(n)
         assert image_metrics(img, ref)["max"] < 1e-4, (W, H)
+
+
+def test_pass_ranges_add_up_to_the_full_render_and_match_the_oracle():
+    """ptb_params.pass_first / pass_count: consecutive ranges of sample passes are exactly the full render's samples
+    (same R2 offsets pixel + pass * spp), so their per-pixel sums add up to the full sums and their ray counts to the
+    full count; a leading range equals the oracle's render of its first passes."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import pyoracle as O
+    W, H, spp, mb = 96, 48, 8, 6
+    scene = P.shirley_spheres(W, H)
+    integ = P.Integrator(scene, W, H, spp, mb)
+    full = integ.render(flags=capi.PTB_FLAG_NO_FILTER).copy()
+    full_rays, full_paths = int(integ.stats.rays), int(integ.stats.paths)
+    parts, rays, paths = [], 0, 0
+    for rng in ((0, 3), (3, 4), (7, 0)):  # (7, 0): count 0 = the rest
+        parts.append(integ.render(flags=capi.PTB_FLAG_NO_FILTER, passes=rng).copy())
+        rays, paths = rays + int(integ.stats.rays), paths + int(integ.stats.paths)
+    assert rays == full_rays and paths == full_paths == W * H * spp
+    assert np.abs(sum(parts) - full).max() <= 1e-4 * max(1.0, full.max())
+    orc = O.OracleScene(scene.tables())
+    ref3, cn3 = orc.render(integ.params, n_threads=4, pass_limit=3, flags=capi.PTB_FLAG_NO_FILTER)
+    ref7, cn7 = orc.render(integ.params, n_threads=4, pass_limit=7, flags=capi.PTB_FLAG_NO_FILTER)
+    assert np.sqrt(np.mean((parts[0] - ref3) ** 2)) < 0.02 and abs(parts[0].mean() - ref3.mean()) < 2e-3
+    assert np.sqrt(np.mean((parts[1] - (ref7 - ref3)) ** 2)) < 0.03
+    # a partial render to an image is normalised by its own passes: a preview, not a darker frame
+    prev = integ.render(passes=(0, 2))
+    assert abs(prev.mean() - integ.render().mean()) < 0.02
+    # float64 mode: the first three passes take exactly the oracle's decisions
+    integ.render(flags=capi.PTB_FLAG_F64 | capi.PTB_FLAG_NO_FILTER, passes=(0, 3))
+    assert list(integ.stats.rays_by_bounce[:mb]) == list(cn3.rays_by_bounce[:mb])
+    for bad in ((8, 0), (-1, 2), (5, 4)):
+        with pytest.raises(capi.PtbError):
+            integ.render(passes=bad)
+
+
+def test_progressive_render_equals_the_one_call_render():
+    W, H, spp, mb = 120, 60, 16, 8
+    integ = P.Integrator(P.shirley_spheres(W, H), W, H, spp, mb)
+    whole = integ.render().copy()
+    whole_rays = int(integ.stats.rays)
+    seen = []
+    img = integ.render_progressive(5, on_preview=lambda im, done: seen.append((done, float(im.mean()))))
+    assert [d for d, _ in seen] == [5, 10, 15, 16]
+    assert int(integ.stats.rays) == whole_rays
+    assert np.abs(img - whole).max() < 1e-4
+    # every preview is a full-brightness image of the passes so far
+    assert all(abs(m - seen[-1][1]) < 0.02 for _, m in seen)

@@ -111,6 +111,21 @@ def test_cli_shirley_writes_the_same_image_as_the_library(tmp_path):
 
 
 @pytest.mark.gpu
+def test_cli_preview_every_rewrites_the_output_and_ends_on_the_same_image(tmp_path):
+    """--preview-every=K: the output file is rewritten after every K sample passes; the last write is the image of
+    the plain run (same samples; the batches' sums are added in float64 on the host)."""
+    a, b = tmp_path / "plain.png", tmp_path / "prog.png"
+    common = ["--dimension=160,80", "--samples-per-pixel=9", "--max-ray-bounces=6"]
+    r1 = subprocess.run([os.path.join(BIN, "shirley_spheres")] + common + ["-o", str(a), "--no-progress"], capture_output=True, text=True)
+    r2 = subprocess.run([os.path.join(BIN, "shirley_spheres")] + common + ["-o", str(b), "--preview-every=4"], capture_output=True, text=True)
+    assert r1.returncode == 0 and r2.returncode == 0, r1.stderr + r2.stderr
+    assert [l for l in r2.stderr.replace("\r", "\n").splitlines() if l.startswith("preview:")] == [
+        f"preview: {k} of 9 passes written to {b}" for k in (4, 8, 9)]
+    x, y = _read_png(a), _read_png(b)
+    assert np.abs(x.astype(int) - y.astype(int)).max() <= 1 and np.mean(x != y) < 2e-3
+
+
+@pytest.mark.gpu
 def test_cli_ganesha_from_a_ply_file_equals_the_in_memory_mesh(tmp_path):
     xyz, faces = P.synthetic_mesh(20000)
     ply = tmp_path / "g.ply"
