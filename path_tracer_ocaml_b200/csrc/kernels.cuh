@@ -1325,7 +1325,10 @@ __global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, SM
     unsigned act = active;
     int keep_r = keep;
     asm volatile("" : "+r"(keep_r));  // loop-invariant: keep it in a register instead of re-deriving it
-    if constexpr (!SMEM && sizeof(R) == 4) {
+    // (render pipeline only: its camera rays are coherent and its launches latency-bound, +8 % on the C3 meshes; the
+    // caller-supplied rays of ptb_intersect_batch keep the phase structure below — with one fetch per step they lose
+    // 3-25 %, most on mid-size scenes that live in L1/L2, where the instruction count decides)
+    if constexpr (!SMEM && sizeof(R) == 4 && MODE == 0) {
       do {
         fused_step_g<MODE == 0, UNIT, true>(L, S, K, sp_limit);
         if (L.cur == TRAV_POP) pop_phase<R, true>(L, K);

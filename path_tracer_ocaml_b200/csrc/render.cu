@@ -354,8 +354,9 @@ static GenConst make_gen(const RenderConst &rc, const int32_t *pixel_list, int p
   return g;
 }
 
+// want_records: the caller runs the render pipeline, whose global-memory traversal reads the 256-bit load records
 template <class R>
-static DScene<R> make_dscene(ptb_scene *s, size_t *scene_bytes_out) {
+static DScene<R> make_dscene(ptb_scene *s, size_t *scene_bytes_out, bool want_records = false) {
   DeviceState *d = s->dev;
   Tables<R> &t = d->tables<R>();
   DScene<R> sc;
@@ -382,7 +383,7 @@ static DScene<R> make_dscene(ptb_scene *s, size_t *scene_bytes_out) {
     sc.light_o[i] = (R)s->host.light_o[i], sc.light_u[i] = (R)s->host.light_u[i], sc.light_v[i] = (R)s->host.light_v[i];
   *scene_bytes_out = sc.scene_in_smem ? bytes : 0;
   if constexpr (sizeof(R) == 4) {
-    if (!sc.scene_in_smem) {  // first use of a committed global-memory scene: its 256-bit load records
+    if (!sc.scene_in_smem && want_records) {  // first render of a committed global-memory scene: its 256-bit load records
       // (+2 triangle records: the fetch of a leaf's last triangle reads the record after it as well)
       if (!t.nodes_g && tbl_alloc((void **)&t.nodes_g, (size_t)sc.n_nodes * sizeof(NodeG)) == cudaSuccess &&
           tbl_alloc((void **)&t.tris_g, ((size_t)sc.n_tris + 2) * sizeof(TriG)) == cudaSuccess &&
@@ -412,7 +413,7 @@ template <class R, int MODE>
 static int trace_config(DeviceState *d, const DScene<R> &sc, size_t scene_bytes, TraceLaunch *tl) {
   const size_t per_thread = trace_smem_per_thread<R>(sc.stack_cap, sc.scene_in_smem != 0);  // (stack +) payload + warp record
   tl->scene_smem = sc.scene_in_smem != 0;
-  if (sizeof(R) == 4 && !tl->scene_smem && !sc.nodes_g)
+  if (sizeof(R) == 4 && MODE == 0 && !tl->scene_smem && !sc.nodes_g)
     return fail(PTB_E_NOMEM, "trace: could not build the global-memory scene records (NodeG / TriG)");
   if (tl->scene_smem) {
     tl->block = sizeof(R) == 8 ? 512 : 1024;  // = the kernel's __launch_bounds__
@@ -527,7 +528,7 @@ static int render_impl(ptb_scene *s, const ptb_params &p, R *d_sums, cudaStream_
   Work<R> &w = pl->work<R>();
   Ctl *ctl = pl->ctl;
   size_t scene_bytes = 0;
-  DScene<R> sc = make_dscene<R>(s, &scene_bytes);
+  DScene<R> sc = make_dscene<R>(s, &scene_bytes, true);
   TraceLaunch tl;
   if ((rc = trace_config<R, 0>(d, sc, scene_bytes, &tl))) return rc;
   const bool profile = (p.flags & PTB_FLAG_PROFILE) != 0;

@@ -59,18 +59,32 @@ def bytes_per_ray(*keys):
         return None
 
 
-def roofline(rays_per_s, cn, b_dram):
+# Lane-divergent loads (every lane of a warp at its own node / primitive record of a scene in global memory) go through
+# the SM's L1 data pipe at ONE lane per cycle for 4-16 bytes and 0.75 lanes per cycle for 32 bytes, texture path
+# included (scripts/microbench/gather.cu, profiles/r2_gather_microbench_48MB.log): at most 24 B per cycle per SM
+# = 6.7 TB/s of useful record bytes on 148 SMs at 1.9 GHz, well below what L2 can deliver.
+L1_GATHER_PEAK = 6.71e12
+B_BOX, B_SPH, B_TRI = 28.0, 16.0, 36.0  # algorithmic record bytes: 6 planes + child reference, (c, r), 9 floats
+
+
+def roofline(rays_per_s, cn, b_dram, gather=False):
     """bound = min(P_issue / A_ray, BW_hbm / B_ray); A_ray from the oracle's reference-faithful counts of
-    the same rays (box x 25 + sphere x 34 + triangle x 46 lane-ops), B_ray = DRAM bytes per ray measured with ncu."""
+    the same rays (box x 25 + sphere x 34 + triangle x 46 lane-ops), B_ray = DRAM bytes per ray measured with ncu.
+    gather: the scene is traversed out of global memory by divergent lanes, which adds the L1 gather bound
+    L1_GATHER_PEAK / (algorithmic record bytes per ray)."""
     rays = max(int(cn.rays), 1)
     a = (cn.box_tests * C_BOX + cn.sphere_tests * C_SPH + cn.tri_tests * C_TRI) / rays
     issue = fp32_peak() / a if a > 0 else None
     hbm = hbm_peak() / b_dram if b_dram else None
-    bound = min(x for x in (issue, hbm) if x is not None)
+    b_rec = (cn.box_tests * B_BOX + cn.sphere_tests * B_SPH + cn.tri_tests * B_TRI) / rays
+    l1 = L1_GATHER_PEAK / b_rec if gather and b_rec > 0 else None
+    bounds = {"fp32_issue": issue, "hbm": hbm, "l1_gather": l1}
+    name = min((k for k in bounds if bounds[k] is not None), key=lambda k: bounds[k])
+    bound = bounds[name]
     return {"a_ray_lane_ops": a, "box_per_ray": cn.box_tests / rays, "sphere_per_ray": cn.sphere_tests / rays,
-            "tri_per_ray": cn.tri_tests / rays, "b_ray_dram_bytes": b_dram, "issue_bound_rays_per_s": issue,
-            "hbm_bound_rays_per_s": hbm, "bound": "fp32_issue" if bound == issue else "hbm", "bound_rays_per_s": bound,
-            "achieved_rays_per_s": rays_per_s, "frac": rays_per_s / bound}
+            "tri_per_ray": cn.tri_tests / rays, "b_ray_dram_bytes": b_dram, "record_bytes_per_ray": b_rec,
+            "issue_bound_rays_per_s": issue, "hbm_bound_rays_per_s": hbm, "l1_gather_bound_rays_per_s": l1,
+            "bound": name, "bound_rays_per_s": bound, "achieved_rays_per_s": rays_per_s, "frac": rays_per_s / bound}
 
 
 def pinned_like(a):
@@ -204,7 +218,9 @@ def sweep(quick):
                         class _C:  # per-ray counts of the sample, in the shape roofline() reads
                             rays, box_tests, sphere_tests, tri_tests = ns, cn.box_tests, cn.sphere_tests, cn.tri_tests
                         key = {(1_000_000, False): "soup_1m_incoherent", (1_000_000, True): "soup_1m_coherent"}.get((m, coherent))
-                        row["roofline"] = roofline(m_dev / (dev_ms * 1e-3), _C, bytes_per_ray(key) if key else None)
+                        # incoherent rays: every lane at its own record (coherent lanes share cache lines: the gather
+                        # bound does not apply to them as stated)
+                        row["roofline"] = roofline(m_dev / (dev_ms * 1e-3), _C, bytes_per_ray(key) if key else None, gather=not coherent)
                 else:
                     row["cpu_note"] = "no CPU side: the reference tree over 10^7 triangles is not built in a sweep (tests/test_baseline_sizes.py checks this size against an Array_leaf scan and across device builders)"
                 log(json.dumps(row))
