@@ -7,7 +7,7 @@
 A "step" is one full render of the workload.  Workload (config.workload): BASELINE.json configs[3],
 `shirley_spheres 3840x2160, 1024 spp, 8 bounces` — the configuration the metric is quoted on; it fits
 one GPU.  Metric: Mpaths/s = W*H*spp / t_render (Mrays/s is reported beside it), t_render = ray
-generation -> traversal/shading -> (N>1: one NCCL reduce of the per-pixel sums) -> filter+gamma resolve.
+generation -> traversal/shading -> (N>1: reduce-scatter of the per-pixel sums by row bands) -> filter+gamma resolve.
 Scene generation and BVH build/upload are outside `value` (the reference prints them separately,
 shirley_spheres/bin/main.ml:264) and inside `e2e`.
 
@@ -98,7 +98,7 @@ def config_dict(world, spp):
     """The `config` of BOTH arms (the reference arm runs a bounded sample of it, described in cpu_baseline.sample)."""
     return {"workload": WORKLOAD if spp == SPP else f"DEV OVERRIDE spp={spp}: " + WORKLOAD,
             "sharding": f"reference tile list (Tile.split 1024 px), tile t -> rank t mod {world}",
-            "l2": "no flush needed: each wavefront batch (up to 256 Mi paths) streams tens of GB of queue state (>> 126 MB L2)",
+            "l2": "no flush needed: each wavefront batch (up to 512 Mi paths) streams tens of GB of queue state (>> 126 MB L2)",
             "paths_per_step": W * H * spp}
 
 
