@@ -49,7 +49,19 @@ struct alignas(128) NodeG {
 struct alignas(64) TriG {
   float v[16];  // v0, e1, e2 (9 floats); the rest is padding
 };
-static_assert(sizeof(NodeG) == 128 && sizeof(TriG) == 64, "256-bit load records");
+// The same node with 8-bit child boxes, 64 B = two 256-bit loads, for caller-supplied (incoherent) rays, whose traversal
+// is bound by the bytes each lane gathers: plane = origin + q * s per axis, q in [0, 255], s a power of two, the low
+// planes rounded down and the high planes rounded up with a margin that covers the decode arithmetic (render.cu /
+// k_make_g_layout).  scale15 = s * 2^15: the kernel turns a byte into the float 1 + q * 2^-15 with one PRMT.
+// An unused child slot has q_lo = 255 > q_hi = 0 on every axis: an inverted box, which every ray misses.
+struct alignas(64) NodeQ {
+  float origin[3];
+  float scale15[3];
+  uint32_t qlo[3];  // one byte per child
+  uint32_t qhi[3];
+  int32_t child[4];
+};
+static_assert(sizeof(NodeG) == 128 && sizeof(TriG) == 64 && sizeof(NodeQ) == 64, "256-bit load records");
 
 struct alignas(16) DMat {
   int32_t kind;
@@ -74,6 +86,7 @@ struct DScene {
   const Vec4<R> *tris;     // 3 per slot: (v0,_), (e1,_), (e2,_)
   const NodeG *nodes_g;    // float scenes in global memory: the same tree and triangles as 256-bit load records
   const TriG *tris_g;
+  const NodeQ *nodes_q;    // ... and with quantised child boxes (ptb_intersect_batch)
   const Vec4<R> *spheres_g;  // (cx, cy, cz, r^2), padded by 8 records
   const int32_t *sphere_id, *tri_id;    // slot -> caller index
   const int32_t *sphere_mat, *tri_mat;  // slot -> material row

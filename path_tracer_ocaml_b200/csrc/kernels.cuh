@@ -453,6 +453,7 @@ struct SceneRef {
   const char *g_nodes;
   const Vec4<R> *g_spheres, *g_tris;
   const char *g_nodes_g, *g_tris_g, *g_sph_g;  // float, global memory: NodeG / TriG records, spheres as (c, r^2)
+  const char *g_nodes_q;                       // NodeQ records
   const uint8_t *g_kinds;
   static constexpr unsigned ROW = 4u * (unsigned)sizeof(R);  // one SoA row of a node: 4 children of one plane
   // material kind of a primitive; `best` = slot | type << 30; table = spheres then triangles
@@ -526,7 +527,8 @@ struct Lane {
 
 // UNIT: unit-length direction, a = 1 is not stored (float render pipeline).  root: the root's `cur` value (node
 // index 0, or its shared-memory address when the staged tree holds addresses)
-template <class R, bool UNIT = false>
+// QM: onx / ony / onz hold all-ones masks for negative direction components instead of row offsets (NodeQ traversal)
+template <class R, bool UNIT = false, bool QM = false>
 __device__ __forceinline__ void lane_init(Lane<R> &L, V3<R> o, V3<R> d, R tmin, R tmax, unsigned sp0, int root = 0) {
   constexpr unsigned ROW = 4u * (unsigned)sizeof(R);
   if constexpr (sizeof(R) == 4 && UNIT) {
@@ -538,17 +540,27 @@ __device__ __forceinline__ void lane_init(Lane<R> &L, V3<R> o, V3<R> d, R tmin, 
     // reciprocal is -inf) reads its planes in the order its reciprocal implies.  Caller-supplied rays
     // (intersect_batch), where axis-parallel directions are common, keep the guarded form below.
     L.idir = {r_rcp(d.x), r_rcp(d.y), r_rcp(d.z)};
-    L.onx = r2i(d.x) < 0 ? 3u * ROW : 0u;  // rows: lo.x lo.y lo.z hi.x hi.y hi.z
-    L.ony = r2i(d.y) < 0 ? 4u * ROW : ROW;
-    L.onz = r2i(d.z) < 0 ? 5u * ROW : 2u * ROW;
+    if constexpr (QM) {
+      L.onx = (unsigned)(r2i(d.x) >> 31), L.ony = (unsigned)(r2i(d.y) >> 31), L.onz = (unsigned)(r2i(d.z) >> 31);
+    } else {
+      L.onx = r2i(d.x) < 0 ? 3u * ROW : 0u;  // rows: lo.x lo.y lo.z hi.x hi.y hi.z
+      L.ony = r2i(d.y) < 0 ? 4u * ROW : ROW;
+      L.onz = r2i(d.z) < 0 ? 5u * ROW : 2u * ROW;
+    }
   } else {
     auto safe_rcp = [](R x) {
       return (r_abs(x) < Lim<R>::tiny()) ? r_copysign(R(1) / Lim<R>::tiny(), x) : r_rcp(x);
     };
     L.idir = {safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z)};
-    L.onx = d.x >= R(0) ? 0u : 3u * ROW;  // rows: lo.x lo.y lo.z hi.x hi.y hi.z
-    L.ony = d.y >= R(0) ? ROW : 4u * ROW;
-    L.onz = d.z >= R(0) ? 2u * ROW : 5u * ROW;
+    if constexpr (QM) {
+      L.onx = d.x >= R(0) ? 0u : 0xffffffffu;
+      L.ony = d.y >= R(0) ? 0u : 0xffffffffu;
+      L.onz = d.z >= R(0) ? 0u : 0xffffffffu;
+    } else {
+      L.onx = d.x >= R(0) ? 0u : 3u * ROW;  // rows: lo.x lo.y lo.z hi.x hi.y hi.z
+      L.ony = d.y >= R(0) ? ROW : 4u * ROW;
+      L.onz = d.z >= R(0) ? 2u * ROW : 5u * ROW;
+    }
   }
   L.oid = {o.x * L.idir.x, o.y * L.idir.y, o.z * L.idir.z};
   if constexpr (sizeof(R) == 4) {
@@ -706,6 +718,15 @@ __device__ __forceinline__ void leaf_phase(Lane<R> &L, const SceneRef<R, SMEM> &
 #pragma unroll 1
     for (int i = 0; i < cnt; ++i)
       sphere_test(S.sphere(first + i), L.o, L.d, UNIT ? R(1) : L.a, UNIT ? R(1) : L.inv_a, tmin, L.tbest, L.best, first + i);
+  } else if constexpr (!SMEM && sizeof(R) == 4) {
+    const char *tp = S.g_tris_g + (size_t)(unsigned)first * sizeof(TriG);  // 32 + 4 bytes per triangle instead of 3 x 16
+#pragma unroll 1
+    for (int i = 0; i < cnt; ++i, tp += sizeof(TriG)) {
+      const F8 a = ldg256(tp);
+      const float e2z = __ldg(reinterpret_cast<const float *>(tp + 32));
+      tri_test<R>(Vec4<R>{a.v[0], a.v[1], a.v[2], 0.f}, Vec4<R>{a.v[3], a.v[4], a.v[5], 0.f}, Vec4<R>{a.v[6], a.v[7], e2z, 0.f},
+                  L.o, L.d, tmin, L.tbest, L.best, (first + i) | (1 << 30));
+    }
   } else {
 #pragma unroll 1
     for (int i = 0; i < cnt; ++i)
@@ -724,6 +745,88 @@ __device__ __forceinline__ void pop_phase(Lane<R> &L, const Stack<R, LOCAL> &K) 
     L.sp -= K.stride;
     K.load(L.sp, L.cur, t);
   } while (t > L.tbest);
+}
+
+// Node visit on NodeQ records (float, global memory, caller-supplied rays): two 256-bit loads instead of seven 128-bit
+// ones.  Per axis the near / far byte words are picked by the direction's sign mask (one LOP3 each), every byte
+// becomes the float 1 + q * 2^-15 with one PRMT, and its plane distance is one FFMA:
+//   t = (origin + q s - o) / d = f * S + B,  S = s 2^15 / d,  B = origin / d - o / d - S.
+template <bool TMIN0, bool CHECK>
+__device__ __forceinline__ void node_q_math(Lane<float> &L, Stack<float, true> &K, unsigned sp_limit, const F8 &H0, const F8 &H1) {
+  const unsigned lox = __float_as_uint(H0.v[6]), loy = __float_as_uint(H0.v[7]), loz = __float_as_uint(H1.v[0]);
+  const unsigned hix = __float_as_uint(H1.v[1]), hiy = __float_as_uint(H1.v[2]), hiz = __float_as_uint(H1.v[3]);
+  const int4 ch = {__float_as_int(H1.v[4]), __float_as_int(H1.v[5]), __float_as_int(H1.v[6]), __float_as_int(H1.v[7])};
+  const float Sx = H0.v[3] * L.idir.x, Sy = H0.v[4] * L.idir.y, Sz = H0.v[5] * L.idir.z;
+  const float Bx = fmaf(H0.v[0], L.idir.x, -L.oid.x) - Sx, By = fmaf(H0.v[1], L.idir.y, -L.oid.y) - Sy,
+              Bz = fmaf(H0.v[2], L.idir.z, -L.oid.z) - Sz;
+  const unsigned nwx = (lox & ~L.onx) | (hix & L.onx), fwx = (hix & ~L.onx) | (lox & L.onx);
+  const unsigned nwy = (loy & ~L.ony) | (hiy & L.ony), fwy = (hiy & ~L.ony) | (loy & L.ony);
+  const unsigned nwz = (loz & ~L.onz) | (hiz & L.onz), fwz = (hiz & ~L.onz) | (loz & L.onz);
+  const float tmin = TMIN0 ? 0.0f : L.tmin;
+  float tnx, tny, tnz, tnw;
+#define PTB_QF(w, k) __uint_as_float(__byte_perm(w, 0x3F800000u, 0x7604u | ((k) << 4)))
+#define PTB_SLAB(o, k)                                                                                               \
+  tn##o = fmaxf(fmaxf(fmaf(PTB_QF(nwx, k), Sx, Bx), fmaf(PTB_QF(nwy, k), Sy, By)), fmaxf(fmaf(PTB_QF(nwz, k), Sz, Bz), tmin)); \
+  {                                                                                                                  \
+    const float tf_ = fminf(fminf(fmaf(PTB_QF(fwx, k), Sx, Bx), fmaf(PTB_QF(fwy, k), Sy, By)), fmaf(PTB_QF(fwz, k), Sz, Bz)); \
+    asm("{\n.reg .pred p;\nsetp.gtu.f32 p, %0, %1;\n@p add.f32 %0, %0, 0f7F800000;\n}" : "+f"(tn##o) : "f"(tf_));    \
+  }
+  PTB_SLAB(x, 0u)
+  PTB_SLAB(y, 1u)
+  PTB_SLAB(z, 2u)
+  PTB_SLAB(w, 3u)
+#undef PTB_SLAB
+#undef PTB_QF
+  node_finish<float, false, CHECK>(L, K, sp_limit, tnx, tny, tnz, tnw, ch);
+}
+template <bool CHECK>
+__device__ __forceinline__ void node_phase_q(Lane<float> &L, const SceneRef<float, false> &S, Stack<float, true> &K,
+                                             unsigned sp_limit) {
+  const char *np = S.g_nodes_q + (size_t)(unsigned)L.cur * sizeof(NodeQ);
+  const F8 H0 = ldg256(np), H1 = ldg256(np + 32);
+  node_q_math<false, CHECK>(L, K, sp_limit, H0, H1);
+}
+
+// One traversal step per lane and iteration on 64-byte records (see fused_step_g below for the idea): a NodeQ node,
+// ONE triangle (TriG), or the spheres of a leaf that lie in the 64 bytes fetched (3 or 4).
+template <bool TMIN0, bool UNIT, bool CHECK>
+__device__ __forceinline__ void fused_step_q(Lane<float> &L, const SceneRef<float, false> &S, Stack<float, true> &K,
+                                             unsigned sp_limit) {
+  const int cur = L.cur;
+  if (cur <= TRAV_POP) return;  // (idle, finished)
+  const unsigned code = ~(unsigned)cur;
+  const bool is_tri = ((code >> 30) & 1u) != 0u;
+  const unsigned first = code & 0x3FFFFFFu;
+  const char *p = cur >= 0 ? S.g_nodes_q + (size_t)(unsigned)cur * sizeof(NodeQ)
+                           : (is_tri ? S.g_tris_g + (size_t)first * sizeof(TriG)
+                                     : S.g_sph_g + (size_t)(first & ~1u) * sizeof(Vec4<float>));
+  const F8 H0 = ldg256(p), H1 = ldg256(p + 32);
+  if (cur >= 0) {
+    node_q_math<TMIN0, CHECK>(L, K, sp_limit, H0, H1);
+    return;
+  }
+  const float tmin = TMIN0 ? 0.0f : L.tmin;
+  const unsigned cnt = ((code >> 26) & 15u) + 1u;
+  if (is_tri) {
+    tri_test<float>(Vec4<float>{H0.v[0], H0.v[1], H0.v[2], 0.f}, Vec4<float>{H0.v[3], H0.v[4], H0.v[5], 0.f},
+                    Vec4<float>{H0.v[6], H0.v[7], H1.v[0], 0.f}, L.o, L.d, tmin, L.tbest, L.best, (int)(first | (1u << 30)));
+    L.cur = cnt <= 1u ? TRAV_POP : (int)~(code + 1u - (1u << 26));  // (first += 1, count -= 1)
+  } else {
+    // records (first & ~1) .. +3 are in; the leaf starts at the first or the second of them
+    const bool odd = (first & 1u) != 0u;
+    const unsigned here = min(cnt, odd ? 3u : 4u);
+    const float a = UNIT ? 1.0f : L.a, inv_a = UNIT ? 1.0f : L.inv_a;
+#define PTB_SPH(k, e0, e1, e2, e3, o0, o1, o2, o3)                                                              \
+  if (here > k)                                                                                                   \
+    sphere_test(odd ? Vec4<float>{o0, o1, o2, o3} : Vec4<float>{e0, e1, e2, e3}, L.o, L.d, a, inv_a, tmin, L.tbest, \
+                L.best, (int)(first + k));
+    PTB_SPH(0u, H0.v[0], H0.v[1], H0.v[2], H0.v[3], H0.v[4], H0.v[5], H0.v[6], H0.v[7])
+    PTB_SPH(1u, H0.v[4], H0.v[5], H0.v[6], H0.v[7], H1.v[0], H1.v[1], H1.v[2], H1.v[3])
+    PTB_SPH(2u, H1.v[0], H1.v[1], H1.v[2], H1.v[3], H1.v[4], H1.v[5], H1.v[6], H1.v[7])
+    PTB_SPH(3u, H1.v[4], H1.v[5], H1.v[6], H1.v[7], H1.v[4], H1.v[5], H1.v[6], H1.v[7])
+#undef PTB_SPH
+    L.cur = cnt <= here ? TRAV_POP : (int)~(code + here - (here << 26));
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -983,6 +1086,13 @@ __host__ __device__ constexpr size_t trace_smem_per_thread(int stack_cap, bool s
          (WS_WORDS * 4u + 31u) / 32u + RING * 2u * sizeof(Vec4<R>) / 32u;
 }
 
+#ifndef PTB_GLOBAL_RENDER_LOOP
+#define PTB_GLOBAL_RENDER_LOOP 1
+#endif
+#ifndef PTB_GLOBAL_BATCH_LOOP
+#define PTB_GLOBAL_BATCH_LOOP 2
+#endif
+
 // GEN: bounce 0 — the rays are the camera samples [0, gen_n) of the batch, generated in registers
 // (camera_sample) instead of being read from `rays`.
 // BLK: the block size when it is known at compile time (the 1024-thread float launch of shared-memory scenes: the
@@ -1007,6 +1117,7 @@ __global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, SM
   S.g_nodes = reinterpret_cast<const char *>(sc.nodes), S.g_spheres = sc.spheres, S.g_tris = sc.tris;
   S.g_nodes_g = reinterpret_cast<const char *>(sc.nodes_g), S.g_tris_g = reinterpret_cast<const char *>(sc.tris_g);
   S.g_sph_g = reinterpret_cast<const char *>(sc.spheres_g);
+  S.g_nodes_q = reinterpret_cast<const char *>(sc.nodes_q);
   S.g_kinds = sc.prim_kind;
   unsigned scene_bytes = 0;
   if (SMEM) {
@@ -1082,6 +1193,10 @@ __global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, SM
   if (lane == WS_ROOT) sts_i32(ws + WS_ROOT * 4u, SMEM ? (int)smem_base : 0);     // read back at every refill
   __syncwarp();
   constexpr bool UNIT = MODE == 0 && sizeof(R) == 4;  // render pipeline, float: unit directions (sphere_test_f)
+  // traversal loop of a float scene in global memory: 0 = phases on Node4 records, 1 = one 112-byte fetch per step
+  // (NodeG), 2 = phases on quantised NodeQ records, 3 = one 64-byte fetch per step (NodeQ)
+  constexpr int GLOOP = (SMEM || sizeof(R) != 4) ? 0 : (MODE == 0 ? PTB_GLOBAL_RENDER_LOOP : PTB_GLOBAL_BATCH_LOOP);
+  constexpr bool QM = GLOOP >= 2;  // the lane keeps direction-sign masks instead of row offsets
   constexpr unsigned VB = (unsigned)sizeof(Vec4<R>);
   // staging ring of this warp: RING origins, then RING directions (entry i of the queue sits in slot i % RING)
   const unsigned ring_a = pay_base + nthreads * (unsigned)(sizeof(Vec4<R>) + sizeof(R) + 4u) + (nthreads >> 5) * (WS_WORDS * 4u) +
@@ -1205,7 +1320,7 @@ __global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, SM
               const Vec4<R> pv = {R(1), R(1), R(1), i2r(pixel, R())};
               sts_vec4(pay_v, pv);
               sts_r(pay_r, i2r(offset, R()));
-              lane_init<R, UNIT>(L, V3<R>{R(0), R(0), R(0)}, dir, R(0), Lim<R>::tmax(), sp0r, root);
+              lane_init<R, UNIT, QM>(L, V3<R>{R(0), R(0), R(0)}, dir, R(0), Lim<R>::tmax(), sp0r, root);
             } else {
               const Vec4<R> A = lds_vec4(ring_a + (ray_i % RING) * VB, R()), B = lds_vec4(ring_b + (ray_i % RING) * VB, R());
               if (MODE == 0) {
@@ -1213,7 +1328,7 @@ __global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, SM
                 cp_async_vec4<R, 2>(pay_v, rays.A(ray_i));
                 sts_r(pay_r, B.w);
               }
-              lane_init<R, UNIT>(L, V3<R>{A.x, A.y, A.z}, V3<R>{B.x, B.y, B.z}, (MODE == 0) ? R(0) : tmin_arg,
+              lane_init<R, UNIT, QM>(L, V3<R>{A.x, A.y, A.z}, V3<R>{B.x, B.y, B.z}, (MODE == 0) ? R(0) : tmin_arg,
                                  (MODE == 0) ? Lim<R>::tmax() : tmax_arg, sp0r, root);
             }
             // (Visiting the root right here, for all refilled lanes at once — broadcast shared-memory reads, no loop
@@ -1325,18 +1440,25 @@ __global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, SM
     unsigned act = active;
     int keep_r = keep;
     asm volatile("" : "+r"(keep_r));  // loop-invariant: keep it in a register instead of re-deriving it
-    // (render pipeline only: its camera rays are coherent and its launches latency-bound, +8 % on the C3 meshes; the
-    // caller-supplied rays of ptb_intersect_batch keep the phase structure below — with one fetch per step they lose
-    // 3-25 %, most on mid-size scenes that live in L1/L2, where the instruction count decides)
-    if constexpr (!SMEM && sizeof(R) == 4 && MODE == 0) {
+    if constexpr (GLOOP == 1) {
       do {
         fused_step_g<MODE == 0, UNIT, true>(L, S, K, sp_limit);
         if (L.cur == TRAV_POP) pop_phase<R, true>(L, K);
         act = __ballot_sync(0xffffffffu, L.cur > TRAV_DONE);
       } while (__popc(act) >= keep_r);
+    } else if constexpr (GLOOP == 3) {
+      do {
+        fused_step_q<MODE == 0, UNIT, true>(L, S, K, sp_limit);
+        if (L.cur == TRAV_POP) pop_phase<R, true>(L, K);
+        act = __ballot_sync(0xffffffffu, L.cur > TRAV_DONE);
+      } while (__popc(act) >= keep_r);
     } else
     do {
-      if (L.cur >= 0) node_phase<R, SMEM, MODE == 0, sizeof(R) == 8, !SMEM>(L, S, K, sp_limit);
+      if constexpr (GLOOP == 2) {
+        if (L.cur >= 0) node_phase_q<true>(L, S, K, sp_limit);
+      } else {
+        if (L.cur >= 0) node_phase<R, SMEM, MODE == 0, sizeof(R) == 8, !SMEM>(L, S, K, sp_limit);
+      }
       const bool at_leaf = (unsigned)(L.cur - (TRAV_POP + 1)) < (unsigned)(0 - (TRAV_POP + 1));  // TRAV_POP < cur < 0
       const unsigned lm = __ballot_sync(0xffffffffu, at_leaf);
       if (__popc(lm) >= LEAF_MIN || lm == act) {  // (lm == 0 never equals act inside the loop)
@@ -1761,7 +1883,7 @@ __global__ void __launch_bounds__(256) k_make_g_layout(const Node4<float> *__res
                                                        const Vec4<float> *__restrict__ tris, int n_tris,
                                                        const Vec4<float> *__restrict__ spheres, int n_spheres,
                                                        NodeG *__restrict__ ng, TriG *__restrict__ tg,
-                                                       Vec4<float> *__restrict__ sg) {
+                                                       Vec4<float> *__restrict__ sg, NodeQ *__restrict__ nq) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_spheres + 8) {  // (c, r^2); the 8 records of padding keep the 112-byte fetch of the last leaf inside the array
     Vec4<float> v = {0.f, 0.f, 0.f, 0.f};
@@ -1777,6 +1899,43 @@ __global__ void __launch_bounds__(256) k_make_g_layout(const Node4<float> *__res
       g.child[k] = n.child[k], g.pad[k] = 0;
     }
     ng[i] = g;
+    // 8-bit child boxes relative to the node's own box.  All of this is exact in double (float origin, power-of-two
+    // step, q <= 255); `margin` covers what the kernel's decode adds to the usual slab rounding: the roundings of
+    // S = s 2^15 / d and of B (about 3e-3 of a step, i.e. < 2.4e-5 of the extent).
+    NodeQ q;
+    for (int a = 0; a < 3; ++a) {
+      double mn = 1e300, mx = -1e300;
+      for (int k = 0; k < 4; ++k)
+        if (n.child[k] != INT32_MIN) mn = fmin(mn, (double)n.lo[a][k]), mx = fmax(mx, (double)n.hi[a][k]);
+      if (mn > mx) mn = mx = 0.0;  // (no children at all: never visited)
+      const double margin = 1e-4 * (mx - mn) + 1e-30;
+      const float org = __double2float_rd(mn - 2.0 * margin);
+      const double need = (mx + margin) - (double)org;
+      int e = -60;
+      if (need > 0.0) {
+        frexp(need / 254.0, &e);  // need / 254 = m 2^e, m in [0.5, 1): 2^e >= need / 254
+        e = max(e, -100);
+      }
+      const double st = ldexp(1.0, e);
+      q.origin[a] = org;
+      q.scale15[a] = (float)ldexp(1.0, e + 15);
+      unsigned wl = 0, wh = 0;
+      for (int k = 0; k < 4; ++k) {
+        unsigned ql = 255u, qh = 0u;  // unused slot: inverted box
+        if (n.child[k] != INT32_MIN) {
+          const double lo = n.lo[a][k], hi = n.hi[a][k];
+          double fl = floor((lo - (double)org) / st);
+          if (lo - ((double)org + fl * st) < margin && fl > 0.0) fl -= 1.0;
+          double ce = ceil((hi - (double)org) / st);
+          if (((double)org + ce * st) - hi < margin) ce += 1.0;
+          ql = (unsigned)fmin(fmax(fl, 0.0), 255.0), qh = (unsigned)fmin(fmax(ce, 0.0), 255.0);
+        }
+        wl |= ql << (8 * k), wh |= qh << (8 * k);
+      }
+      q.qlo[a] = wl, q.qhi[a] = wh;
+    }
+    for (int k = 0; k < 4; ++k) q.child[k] = n.child[k];
+    nq[i] = q;
   }
   if (i < n_tris) {
     const Vec4<float> v0 = tris[3 * (size_t)i], e1 = tris[3 * (size_t)i + 1], e2 = tris[3 * (size_t)i + 2];

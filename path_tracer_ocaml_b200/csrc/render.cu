@@ -33,6 +33,7 @@ struct Tables {
   NodeG *nodes_g = nullptr;  // float scenes that stay in global memory (make_dscene): 256-bit load records
   TriG *tris_g = nullptr;
   Vec4<R> *spheres_g = nullptr;
+  NodeQ *nodes_q = nullptr;
   bool ready = false;
   bool in_blob = false;  // the pointers are slices of DeviceState::blob (freed with it)
 };
@@ -132,7 +133,7 @@ static void tbl_free(void *p) {
 template <class R>
 static void free_tables(Tables<R> &t) {
   if (!t.in_blob) tbl_free(t.nodes), tbl_free(t.spheres), tbl_free(t.tris), tbl_free(t.tri_uv), tbl_free(t.texs);
-  tbl_free(t.nodes_g), tbl_free(t.tris_g), tbl_free(t.spheres_g);
+  tbl_free(t.nodes_g), tbl_free(t.tris_g), tbl_free(t.spheres_g), tbl_free(t.nodes_q);
   t = Tables<R>();
 }
 template <class R>
@@ -383,19 +384,21 @@ static DScene<R> make_dscene(ptb_scene *s, size_t *scene_bytes_out, bool want_re
     sc.light_o[i] = (R)s->host.light_o[i], sc.light_u[i] = (R)s->host.light_u[i], sc.light_v[i] = (R)s->host.light_v[i];
   *scene_bytes_out = sc.scene_in_smem ? bytes : 0;
   if constexpr (sizeof(R) == 4) {
-    if (!sc.scene_in_smem && want_records) {  // first render of a committed global-memory scene: its 256-bit load records
+    if (!sc.scene_in_smem) {  // first use of a committed global-memory scene: its 256-bit load records
       // (+2 triangle records: the fetch of a leaf's last triangle reads the record after it as well)
       if (!t.nodes_g && tbl_alloc((void **)&t.nodes_g, (size_t)sc.n_nodes * sizeof(NodeG)) == cudaSuccess &&
           tbl_alloc((void **)&t.tris_g, ((size_t)sc.n_tris + 2) * sizeof(TriG)) == cudaSuccess &&
-          tbl_alloc((void **)&t.spheres_g, ((size_t)sc.n_spheres + 8) * sizeof(Vec4<R>)) == cudaSuccess) {
+          tbl_alloc((void **)&t.spheres_g, ((size_t)sc.n_spheres + 8) * sizeof(Vec4<R>)) == cudaSuccess &&
+          tbl_alloc((void **)&t.nodes_q, (size_t)sc.n_nodes * sizeof(NodeQ)) == cudaSuccess) {
         const int n = std::max(std::max(sc.n_nodes, sc.n_tris), sc.n_spheres + 8);
         k_make_g_layout<<<(unsigned)((n + 255) / 256), 256>>>(t.nodes, sc.n_nodes, t.tris, sc.n_tris, t.spheres, sc.n_spheres,
-                                                              t.nodes_g, t.tris_g, t.spheres_g);
+                                                              t.nodes_g, t.tris_g, t.spheres_g, t.nodes_q);
         if (cudaStreamSynchronize(0) != cudaSuccess)
-          tbl_free(t.nodes_g), tbl_free(t.tris_g), tbl_free(t.spheres_g), t.nodes_g = nullptr, t.tris_g = nullptr, t.spheres_g = nullptr;
+          tbl_free(t.nodes_g), tbl_free(t.tris_g), tbl_free(t.spheres_g), tbl_free(t.nodes_q), t.nodes_g = nullptr,
+              t.tris_g = nullptr, t.spheres_g = nullptr, t.nodes_q = nullptr;
       }
-      const bool ok = t.nodes_g && t.tris_g && t.spheres_g;  // (null: trace_config reports the failure)
-      sc.nodes_g = ok ? t.nodes_g : nullptr, sc.tris_g = t.tris_g, sc.spheres_g = t.spheres_g;
+      const bool ok = t.nodes_g && t.tris_g && t.spheres_g && t.nodes_q;  // (null: trace_config reports the failure)
+      sc.nodes_g = ok ? t.nodes_g : nullptr, sc.tris_g = t.tris_g, sc.spheres_g = t.spheres_g, sc.nodes_q = t.nodes_q;
     }
   }
   return sc;
@@ -413,7 +416,7 @@ template <class R, int MODE>
 static int trace_config(DeviceState *d, const DScene<R> &sc, size_t scene_bytes, TraceLaunch *tl) {
   const size_t per_thread = trace_smem_per_thread<R>(sc.stack_cap, sc.scene_in_smem != 0);  // (stack +) payload + warp record
   tl->scene_smem = sc.scene_in_smem != 0;
-  if (sizeof(R) == 4 && MODE == 0 && !tl->scene_smem && !sc.nodes_g)
+  if (sizeof(R) == 4 && !tl->scene_smem && !sc.nodes_g)
     return fail(PTB_E_NOMEM, "trace: could not build the global-memory scene records (NodeG / TriG)");
   if (tl->scene_smem) {
     tl->block = sizeof(R) == 8 ? 512 : 1024;  // = the kernel's __launch_bounds__

@@ -64,7 +64,7 @@ def bytes_per_ray(*keys):
 # included (scripts/microbench/gather.cu, profiles/r2_gather_microbench_48MB.log): at most 24 B per cycle per SM
 # = 6.7 TB/s of useful record bytes on 148 SMs at 1.9 GHz, well below what L2 can deliver.
 L1_GATHER_PEAK = 6.71e12
-B_BOX, B_SPH, B_TRI = 28.0, 16.0, 36.0  # algorithmic record bytes: 6 planes + child reference, (c, r), 9 floats
+B_BOX, B_SPH, B_TRI = 16.0, 16.0, 36.0  # record bytes: a quarter of a 64-byte quantised node, (c, r), 9 floats
 
 
 def roofline(rays_per_s, cn, b_dram, gather=False):
