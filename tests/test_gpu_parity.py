@@ -207,6 +207,53 @@ def test_intersect_batch_matches_oracle(which):
     assert ((t2[ok] >= 0.5) & (t2[ok] <= 2.0)).all()
 
 
+@pytest.mark.parametrize("which", ["mesh", "soup", "sphere_cloud"])
+def test_intersect_batch_axis_parallel_and_scaled_rays_on_global_memory_scenes(which):
+    """Scenes too big for shared memory are traversed through quantised nodes (8-bit child boxes, decoded with the
+    ray's reciprocal direction).  The rays that stress that decode: exactly axis-parallel directions (guarded
+    reciprocals of 1e30 magnitude), directions with two zero components, and directions far from unit length."""
+    rng = np.random.default_rng(5)
+    if which == "mesh":
+        scene = P.synthetic_mesh_scene(20000, 64, 36)
+    elif which == "soup":
+        m = 30000
+        scene = P.Scene()
+        scene.set_textures([capi.Texture(kind=capi.PTB_TEX_SOLID, rgb=(0.5, 0.5, 0.5))])
+        scene.set_materials([capi.Material(kind=capi.PTB_MAT_LAMBERTIAN, texture=0, index=1.0)])
+        a = rng.uniform(-10, 10, size=(m, 3))
+        v = np.concatenate([a, a + rng.normal(scale=0.3, size=(m, 3)), a + rng.normal(scale=0.3, size=(m, 3))])
+        idx = np.stack([np.arange(m), np.arange(m) + m, np.arange(m) + 2 * m], axis=1).astype(np.int32)
+        scene.set_triangles(v[:, 0], v[:, 1], v[:, 2], idx)
+        scene.set_background(capi.PTB_BG_CONSTANT, (1.0, 1.0, 1.0))
+    else:
+        scene = sphere_cloud(20000, 64, 36, with_quad=True)
+    t = scene.tables()
+    pts = [np.stack([t[k][:t["n_vertices"]] for k in ("vx", "vy", "vz")], 1)] if t.get("n_vertices", 0) else []
+    if t["n_spheres"]:
+        pts.append(np.stack([t["xs"], t["ys"], t["zs"]], 1))
+    pts = np.concatenate(pts)
+    lo, hi = np.quantile(pts, 0.02, axis=0), np.quantile(pts, 0.98, axis=0)  # (the floor / ground primitives are huge)
+    n = 60000
+    o = rng.uniform(lo - 0.2 * (hi - lo), hi + 0.2 * (hi - lo), size=(n, 3))
+    d = np.zeros((n, 3))
+    axis = rng.integers(0, 3, n)
+    d[np.arange(n), axis] = rng.choice([-1.0, 1.0], n)       # first third: exactly axis-parallel
+    k = n // 3
+    d[k:2 * k] = rng.normal(size=(k, 3))
+    d[k:2 * k, 0] = 0.0                                       # second third: one zero component ...
+    d[k + k // 2:2 * k, 1] = 0.0                              # ... or two
+    d[2 * k:] = rng.normal(size=(n - 2 * k, 3)) * rng.choice([1e-3, 1.0, 1e3], size=(n - 2 * k, 1))  # scaled
+    d[np.abs(d).sum(1) == 0] = (0.0, 0.0, 1.0)
+    o32, d32 = o.astype(np.float32), d.astype(np.float32)
+    tt, prim = integrator.intersect_batch(scene, o32, d32)
+    tr, pr, _ = O.OracleScene(t).intersect_batch(o32.astype(np.float64), d32.astype(np.float64), n_threads=NCPU)
+    for part, sl in (("axis-parallel", slice(0, k)), ("zero components", slice(k, 2 * k)), ("scaled", slice(2 * k, n))):
+        eq = prim[sl] == pr[sl]
+        assert eq.mean() >= 0.998, (which, part, eq.mean())
+        assert (pr[sl] >= 0).mean() > 0.02, (which, part)
+        assert np.isnan(tt[sl][eq & (pr[sl] < 0)]).all()
+
+
 def test_intersect_batch_empty_and_single():
     scene = P.shirley_spheres(64, 32)
     t, prim = integrator.intersect_batch(scene, np.zeros((0, 3)), np.zeros((0, 3)))
