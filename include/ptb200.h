@@ -242,6 +242,12 @@ int ptb_camera_create(const double eye[3], const double target[3], const double 
 /* Camera.transform (camera.ml:39-43,91) applied in place to n points. */
 int ptb_camera_transform(const double look_at[16], double *xs, double *ys, double *zs, int64_t n);
 
+/* Triangle pre-splitting as both tree builders apply it to soups of overlapping triangles (csrc/presplit.hpp; the
+ * reference's Shape_tree.create, shape_tree.ml:252-263, has one box per shape): the boxes of the pieces of ONE
+ * triangle (v = 9 doubles: corner-major x, y, z) for the cell size `cell` on the grid anchored at `origin`.  Writes
+ * min(count, cap) boxes as lo[3], hi[3] (6 doubles each) and returns the count.  Host only; diagnostic / tests. */
+int ptb_presplit_boxes(const double *v, double cell, const double origin[3], double *boxes, int32_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -78,6 +78,7 @@ SYMBOLS = {
     "ptb_lds_alpha": (C.c_int, [C.c_int32, _dp]),
     "ptb_tile_split": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _ip, _ip, _ip, _ip, C.c_int32]),
     "ptb_filter_binomial": (C.c_int, [C.c_int32, C.c_int32, _dp]),
+    "ptb_presplit_boxes": (C.c_int, [_dp, C.c_double, _dp, _dp, C.c_int32]),
     "ptb_camera_create": (C.c_int, [_dp, _dp, _dp, C.c_double, C.c_double, _dp]),
     "ptb_camera_transform": (C.c_int, [_dp, _dp, _dp, _dp, C.c_int64]),
     # ptb200_scenes.h

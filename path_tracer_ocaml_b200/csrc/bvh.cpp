@@ -19,6 +19,7 @@
 #include <queue>
 #include <thread>
 
+#include "presplit.hpp"
 #include "scene.hpp"
 
 namespace ptb {
@@ -212,6 +213,58 @@ struct BinaryBuilder {
   }
 };
 
+// ---- triangle pre-splitting (presplit.hpp) ---------------------------------------------------------------------
+// Replaces `tri` (one reference per triangle) by at most `max_factor` x as many references, each with the box of one
+// piece of its triangle.  The cell size starts at the mean spacing of the triangles and grows until the budget holds.
+static double presplit_triangles(const HostScene &s, std::vector<PrimRef> &tri, const Box &all, double max_factor) {
+  const size_t n = tri.size();
+  double vol = 1.0;
+  for (int a = 0; a < 3; ++a) vol *= std::max(all.mx[a] - all.mn[a], 1e-12);
+  double h = std::cbrt(vol / (double)n);
+  const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  auto run = [&](double cell, std::vector<PrimRef> *dst) -> size_t {
+    const unsigned nt = (unsigned)std::min<size_t>(hw, std::max<size_t>(1, n / 4096));
+    std::vector<std::vector<PrimRef>> parts(nt);
+    std::vector<size_t> counts(nt, 0);
+    std::vector<std::thread> th;
+    auto work = [&](unsigned t) {
+      size_t c = 0;
+      for (size_t i = n * t / nt; i < n * (t + 1) / nt; ++i) {
+        double v[3][3];
+        for (int k = 0; k < 3; ++k) {
+          const int x = s.tidx[3 * (size_t)tri[i].id + k];
+          v[k][0] = s.vx[x], v[k][1] = s.vy[x], v[k][2] = s.vz[x];
+        }
+        const int32_t id = tri[i].id;
+        c += (size_t)presplit::pieces(v, cell, all.mn, [&](const double lo[3], const double hi[3]) {
+          if (!dst) return;
+          PrimRef r;
+          for (int a = 0; a < 3; ++a) r.box.mn[a] = lo[a], r.box.mx[a] = hi[a], r.c[a] = 0.5 * (lo[a] + hi[a]);
+          r.id = id;
+          parts[t].push_back(r);
+        });
+      }
+      counts[t] = c;
+    };
+    for (unsigned t = 1; t < nt; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto &t : th) t.join();
+    size_t total = 0;
+    for (unsigned t = 0; t < nt; ++t) total += counts[t];
+    if (dst) {
+      dst->clear();
+      dst->reserve(total);
+      for (auto &v : parts) dst->insert(dst->end(), v.begin(), v.end());
+    }
+    return total;
+  };
+  for (int it = 0; it < 40 && (double)run(h, nullptr) > max_factor * (double)n; ++it) h *= 1.1225;
+  std::vector<PrimRef> refs;
+  run(h, &refs);
+  tri.swap(refs);
+  return h;
+}
+
 }  // namespace
 
 void build_wide_bvh(const HostScene &s, WideBVH *out) {
@@ -225,6 +278,7 @@ void build_wide_bvh(const HostScene &s, WideBVH *out) {
   out->nodes.clear();
   out->sphere_order.clear();
   out->tri_order.clear();
+  out->presplit = false;
   std::vector<BinNode> bn;
   std::vector<PrimRef> sph((size_t)s.n_spheres()), tri((size_t)s.n_tris());
   for (size_t i = 0; i < sph.size(); ++i) {
@@ -246,6 +300,27 @@ void build_wide_bvh(const HostScene &s, WideBVH *out) {
     }
     for (int a = 0; a < 3; ++a) p.c[a] = 0.5 * (p.box.mn[a] + p.box.mx[a]);
     p.id = (int32_t)i;
+  }
+  if (tri.size() >= 2) {
+    // how many triangle boxes contain a random point of the scene (presplit.hpp: far below 1 for surface meshes)
+    Box all;
+    all.reset();
+    double vsum = 0.0;
+    for (const PrimRef &p : tri) {
+      all.grow(p.box);
+      vsum += (p.box.mx[0] - p.box.mn[0]) * (p.box.mx[1] - p.box.mn[1]) * (p.box.mx[2] - p.box.mn[2]);
+    }
+    double vol = 1.0;
+    for (int a = 0; a < 3; ++a) vol *= std::max(all.mx[a] - all.mn[a], 1e-12);
+    double f = presplit::budget_factor(vsum / vol);
+    if (const char *e = std::getenv("PTB_BVH_PRESPLIT")) f = std::atof(e);  // 0 / 1: off; > 1: references per triangle allowed
+    // (small scenes are traversed out of shared memory and must stay small)
+    if (f > 1.0 && tri.size() >= 4096 && (double)tri.size() * f < (double)(1 << 26)) {
+      const size_t before = tri.size();
+      const double h = presplit_triangles(s, tri, all, f);
+      out->presplit = tri.size() > before;
+      if (timing) std::fprintf(stderr, "[bvh] presplit: overlap %.2f, %zu -> %zu references, cell %.4g\n", vsum / vol, before, tri.size(), h);
+    }
   }
   // Big inputs: the top of the tree is built on this thread down to ranges of about n / (8 x threads) primitives;
   // those subtrees are independent (disjoint primitive ranges, sorted in place) and are built by a pool of

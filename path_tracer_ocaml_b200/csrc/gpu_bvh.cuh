@@ -14,8 +14,10 @@
 // Closest-hit results do not depend on the tree, so parity with the oracle is unchanged.
 #pragma once
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "device_types.cuh"
+#include "presplit.hpp"
 
 namespace ptb {
 namespace gbvh {
@@ -62,6 +64,73 @@ __global__ void __launch_bounds__(256) k_tri_boxes(const double *__restrict__ vx
     }
     float bmn = bl[k], bmx = bh[k];
     for (int o = 16; o; o >>= 1) {
+      bmn = fminf(bmn, __shfl_xor_sync(0xffffffffu, bmn, o));
+      bmx = fmaxf(bmx, __shfl_xor_sync(0xffffffffu, bmx, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicMin(&cb[0].lo[k], enc_f(mn));
+      atomicMax(&cb[0].hi[k], enc_f(mx));
+      atomicMin(&cb[1].lo[k], enc_f(bmn));
+      atomicMax(&cb[1].hi[k], enc_f(bmx));
+    }
+  }
+}
+// 1b. triangle pre-splitting (presplit.hpp): how many boxes contain a random point (the trigger), pieces per triangle
+// for a cell size, and the pieces' boxes as the builder's primitives
+__global__ void __launch_bounds__(256) k_box_volume_sum(const float4 *__restrict__ blo, const float4 *__restrict__ bhi, int n,
+                                                        double *__restrict__ sum) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double v = 0.0;
+  if (i < n) v = (double)(bhi[i].x - blo[i].x) * (double)(bhi[i].y - blo[i].y) * (double)(bhi[i].z - blo[i].z);
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0 && v > 0.0) atomicAdd(sum, v);
+}
+__device__ __forceinline__ void load_tri(const double *__restrict__ vx, const double *__restrict__ vy, const double *__restrict__ vz,
+                                         const int32_t *__restrict__ idx, int i, double v[3][3]) {
+  for (int k = 0; k < 3; ++k) {
+    const int a = idx[3 * i + k];
+    v[k][0] = vx[a], v[k][1] = vy[a], v[k][2] = vz[a];
+  }
+}
+__global__ void __launch_bounds__(128) k_presplit_count(const double *__restrict__ vx, const double *__restrict__ vy,
+                                                        const double *__restrict__ vz, const int32_t *__restrict__ idx, int n,
+                                                        double cell, double ox, double oy, double oz, int *__restrict__ counts) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double v[3][3];
+  load_tri(vx, vy, vz, idx, i, v);
+  const double org[3] = {ox, oy, oz};
+  counts[i] = presplit::pieces(v, cell, org, [](const double *, const double *) {});
+}
+__global__ void __launch_bounds__(128) k_presplit_emit(const double *__restrict__ vx, const double *__restrict__ vy,
+                                                       const double *__restrict__ vz, const int32_t *__restrict__ idx, int n,
+                                                       double cell, double ox, double oy, double oz, const int *__restrict__ offsets,
+                                                       float4 *__restrict__ blo, float4 *__restrict__ bhi, int32_t *__restrict__ ref_tri) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double v[3][3];
+  load_tri(vx, vy, vz, idx, i, v);
+  const double org[3] = {ox, oy, oz};
+  int r = offsets[i];
+  presplit::pieces(v, cell, org, [&](const double *lo, const double *hi) {
+    blo[r] = make_float4(__double2float_rd(lo[0]), __double2float_rd(lo[1]), __double2float_rd(lo[2]), 0.f);
+    bhi[r] = make_float4(__double2float_ru(hi[0]), __double2float_ru(hi[1]), __double2float_ru(hi[2]), 0.f);
+    ref_tri[r] = i;
+    ++r;
+  });
+}
+// centroid / box bounds of a list of boxes (k_tri_boxes does the same for the triangles' own boxes)
+__global__ void __launch_bounds__(256) k_box_bounds(const float4 *__restrict__ blo, const float4 *__restrict__ bhi, int n, Bounds6 *cb) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool ok = i < n;
+  float bl[3] = {3.0e38f, 3.0e38f, 3.0e38f}, bh[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+  if (ok) bl[0] = blo[i].x, bl[1] = blo[i].y, bl[2] = blo[i].z, bh[0] = bhi[i].x, bh[1] = bhi[i].y, bh[2] = bhi[i].z;
+  for (int k = 0; k < 3; ++k) {
+    const float c = 0.5f * (bl[k] + bh[k]);
+    float mn = ok ? c : 3.0e38f, mx = ok ? c : -3.0e38f, bmn = bl[k], bmx = bh[k];
+    for (int o = 16; o; o >>= 1) {
+      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
       bmn = fminf(bmn, __shfl_xor_sync(0xffffffffu, bmn, o));
       bmx = fmaxf(bmx, __shfl_xor_sync(0xffffffffu, bmx, o));
     }
@@ -240,7 +309,8 @@ __global__ void __launch_bounds__(128) k_collapse_level(const Frontier *__restri
 }
 
 // 7. primitive tables in sorted order (same arithmetic as ensure_tables<float> on the host: edges from the doubles)
-__global__ void __launch_bounds__(256) k_emit_tris(const unsigned *__restrict__ vals, int n, const double *__restrict__ vx,
+__global__ void __launch_bounds__(256) k_emit_tris(const unsigned *__restrict__ vals, int n, const int32_t *__restrict__ ref_tri,
+                                                   const double *__restrict__ vx,
                                                    const double *__restrict__ vy, const double *__restrict__ vz,
                                                    const int32_t *__restrict__ idx, const int32_t *__restrict__ tmat,
                                                    const double *__restrict__ tuv, const uint8_t *__restrict__ mat_kind,
@@ -249,7 +319,7 @@ __global__ void __launch_bounds__(256) k_emit_tris(const unsigned *__restrict__ 
                                                    uint8_t *__restrict__ prim_kind) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  const int i = (int)vals[k];
+  const int i = ref_tri ? ref_tri[vals[k]] : (int)vals[k];  // (pre-split meshes: primitive = a reference to a triangle)
   const int a = idx[3 * i], b = idx[3 * i + 1], c = idx[3 * i + 2];
   tris[3 * (size_t)k + 0] = {(float)vx[a], (float)vy[a], (float)vz[a], 0.f};
   tris[3 * (size_t)k + 1] = {(float)(vx[b] - vx[a]), (float)(vy[b] - vy[a]), (float)(vz[b] - vz[a]), 0.f};

@@ -5,6 +5,7 @@
 #include <cstring>
 #include <string>
 
+#include "presplit.hpp"
 #include "scene.hpp"
 
 namespace ptb {
@@ -115,6 +116,19 @@ int ptb_filter_binomial(int32_t order, int32_t pixel_radius, double *weights) {
   filter_binomial(order, pixel_radius, &w);
   std::memcpy(weights, w.data(), w.size() * sizeof(double));
   return PTB_OK;
+}
+
+int ptb_presplit_boxes(const double *v, double cell, const double origin[3], double *boxes, int32_t cap) {
+  if (!v || !origin || (!boxes && cap > 0) || !(cell > 0.0)) return fail(PTB_E_INVALID, "ptb_presplit_boxes: bad args");
+  double tri[3][3];
+  for (int k = 0; k < 3; ++k)
+    for (int a = 0; a < 3; ++a) tri[k][a] = v[3 * k + a];
+  int n = 0;
+  return presplit::pieces(tri, cell, origin, [&](const double lo[3], const double hi[3]) {
+    if (n < cap)
+      for (int a = 0; a < 3; ++a) boxes[6 * n + a] = lo[a], boxes[6 * n + 3 + a] = hi[a];
+    ++n;
+  });
 }
 
 // Camera.create (camera.ml:58-83) keeps only what Camera.ray and Camera.transform read.

@@ -1042,7 +1042,7 @@ __global__ void __launch_bounds__(256) k_raygen(GenConst g, unsigned n, Queue<R>
     if (dbg_cy) dbg_cy[k] = cy;
     V3<R> dir = normalize(V3<R>{R(ddx), R(ddy), R(-1)});
     Vec4<R> *e = out.A(k);
-    e[0] = {R(0), R(0), R(0), R(0)};
+    e[0] = {R(0), R(0), R(0), i2r((int)k, R())};  // (w: where a MODE 1 traversal writes this ray's result)
     e[SEG] = {dir.x, dir.y, dir.z, i2r(offset, R())};
     e[2 * SEG] = {R(1), R(1), R(1), i2r(pixel, R())};
     if (k % SEG == 0) out.seg_count[k / SEG] = (int32_t)(n - k < (unsigned)SEG ? n - k : (unsigned)SEG);  // dense
@@ -1328,6 +1328,7 @@ __global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, SM
                 cp_async_vec4<R, 2>(pay_v, rays.A(ray_i));
                 sts_r(pay_r, B.w);
               }
+              if (MODE == 1) ray_i = (unsigned)r2i(A.w);  // the caller's index of this ray (the queue may be in sorted order)
               lane_init<R, UNIT, QM>(L, V3<R>{A.x, A.y, A.z}, V3<R>{B.x, B.y, B.z}, (MODE == 0) ? R(0) : tmin_arg,
                                  (MODE == 0) ? Lim<R>::tmax() : tmax_arg, sp0r, root);
             }
@@ -1997,7 +1998,7 @@ __global__ void k_pack_rays(const float *__restrict__ o, const float *__restrict
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Vec4<R> *e = q.A((unsigned)i);
-  e[0] = {R(o[3 * i]), R(o[3 * i + 1]), R(o[3 * i + 2]), R(0)};
+  e[0] = {R(o[3 * i]), R(o[3 * i + 1]), R(o[3 * i + 2]), i2r((int)i, R())};  // w: the result index
   e[SEG] = {R(d[3 * i]), R(d[3 * i + 1]), R(d[3 * i + 2]), R(0)};
   if (i % SEG == 0) q.seg_count[i / SEG] = (int32_t)(n - i < SEG ? n - i : SEG);  // dense
 }

@@ -14,6 +14,7 @@
 #include "handle.hpp"
 #include "kernels.cuh"
 #include "gpu_bvh.cuh"
+#include "ray_sort.cuh"
 
 namespace ptb {
 
@@ -73,6 +74,8 @@ struct DevicePool {
   size_t sums_cap = 0, img_cap = 0;
   void *batch_buf[4] = {nullptr, nullptr, nullptr, nullptr};  // ptb_intersect_batch: origins, directions, t, prim
   size_t batch_cap[4] = {0, 0, 0, 0};
+  void *sort_buf = nullptr;  // ptb_intersect_batch on global-memory scenes: keys + bins of the ray sort (ray_sort.cuh)
+  size_t sort_cap = 0;
   int32_t *pixel_list = nullptr;
   std::vector<int32_t> pixel_list_host;
   int pl_W = 0, pl_H = 0, pl_rank = -1, pl_world = 0, npix = 0;
@@ -769,7 +772,8 @@ static int gpu_build_mesh(ptb_scene *s) {
   using namespace gbvh;
   DeviceState *d = s->dev;
   const HostScene &h = s->host;
-  const int n = (int)h.n_tris();
+  const int nt = (int)h.n_tris();  // triangles; `n` below counts the builder's primitives = references to triangles
+  int n = nt;
   const size_t nv = h.vx.size();
   double *vx = nullptr, *vy = nullptr, *vz = nullptr, *tuv = nullptr;
   int32_t *idx = nullptr, *tmat = nullptr;
@@ -807,14 +811,8 @@ static int gpu_build_mesh(ptb_scene *s) {
     cleanup();          \
     return rc;          \
   }
-  G(A(&vx, nv)) G(A(&vy, nv)) G(A(&vz, nv)) G(A(&idx, 3 * (size_t)n)) G(A(&tmat, (size_t)n)) G(A(&tuv, 6 * (size_t)n))
-  const bool sah = gpu_builder_sah();
-  const size_t nn = sah ? 2 * (size_t)n + 2 : (size_t)n;  // binary nodes
-  G(A(&mkind, h.mat.size())) G(A(&blo, (size_t)n)) G(A(&bhi, (size_t)n)) G(A(&nlo, nn)) G(A(&nhi, nn)) G(A(&cb, 2))
-  G(A(&k0, (size_t)n)) G(A(&k1, (size_t)n)) G(A(&v0, (size_t)n)) G(A(&v1, (size_t)n)) G(A(&visits, nn))
-  G(A(&lch, nn)) G(A(&rch, nn)) G(A(&first, nn)) G(A(&count, nn)) G(A(&pari, nn)) G(A(&parl, nn))
-  G(A(&counters, 4)) G(A(&fa, (size_t)n)) G(A(&fb, (size_t)n)) G(A(&tmp_nodes, (size_t)n))
-  (void)visits;
+  G(A(&vx, nv)) G(A(&vy, nv)) G(A(&vz, nv)) G(A(&idx, 3 * (size_t)nt)) G(A(&tmat, (size_t)nt)) G(A(&tuv, 6 * (size_t)nt))
+  G(A(&mkind, h.mat.size())) G(A(&blo, (size_t)nt)) G(A(&bhi, (size_t)nt)) G(A(&cb, 2))
   auto H2D = [&](void *dst, const void *src, size_t bytes) -> int {
     CK(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
     return PTB_OK;
@@ -822,14 +820,77 @@ static int gpu_build_mesh(ptb_scene *s) {
   std::vector<uint8_t> mk(h.mat.size());
   for (size_t i = 0; i < mk.size(); ++i) mk[i] = queue_kind(h.mat[i].kind);
   G(H2D(vx, h.vx.data(), nv * 8)) G(H2D(vy, h.vy.data(), nv * 8)) G(H2D(vz, h.vz.data(), nv * 8))
-  G(H2D(idx, h.tidx.data(), 3 * (size_t)n * 4)) G(H2D(tmat, h.tmat.data(), (size_t)n * 4)) G(H2D(tuv, h.tuv.data(), 6 * (size_t)n * 8))
+  G(H2D(idx, h.tidx.data(), 3 * (size_t)nt * 4)) G(H2D(tmat, h.tmat.data(), (size_t)nt * 4)) G(H2D(tuv, h.tuv.data(), 6 * (size_t)nt * 8))
   G(H2D(mkind, mk.data(), mk.size()))
   Bounds6 cb0[2];
   for (int q = 0; q < 2; ++q)
     for (int k = 0; k < 3; ++k) cb0[q].lo[k] = 0xffffffffu, cb0[q].hi[k] = 0u;
   G(H2D(cb, cb0, sizeof cb0))
+  k_tri_boxes<<<(unsigned)((nt + 255) / 256), 256>>>(vx, vy, vz, idx, nt, blo, bhi, cb);
+  // Triangle pre-splitting (presplit.hpp): where the triangles' boxes overlap several times over — a soup, not a surface —
+  // the builder gets several references per triangle, each with the box of one piece of it.
+  int32_t *ref_tri = nullptr;  // reference -> triangle (null: the identity)
+  {
+    double *vsum = nullptr;
+    G(A(&vsum, 1))
+    if (cudaMemset(vsum, 0, 8) != cudaSuccess) {
+      cleanup();
+      return fail(PTB_E_CUDA, "gpu build: memset failed");
+    }
+    k_box_volume_sum<<<(unsigned)((nt + 255) / 256), 256>>>(blo, bhi, nt, vsum);
+    Bounds6 hb[2];
+    double hv = 0.0;
+    if (cudaMemcpy(hb, cb, sizeof hb, cudaMemcpyDeviceToHost) != cudaSuccess || cudaMemcpy(&hv, vsum, 8, cudaMemcpyDeviceToHost) != cudaSuccess) {
+      cleanup();
+      return fail(PTB_E_CUDA, "gpu build: box bounds");
+    }
+    double org[3], vol = 1.0;
+    for (int k = 0; k < 3; ++k) {
+      org[k] = (double)dec_f(hb[1].lo[k]);
+      vol *= std::max((double)dec_f(hb[1].hi[k]) - org[k], 1e-12);
+    }
+    double f = presplit::budget_factor(hv / vol);
+    if (const char *e = std::getenv("PTB_BVH_PRESPLIT")) f = std::atof(e);  // 0 / 1: off; > 1: references per triangle allowed
+    if (f > 1.0 && (double)nt * f < (double)(1 << 26)) {
+      int *cnt = nullptr, *off = nullptr;
+      void *scan_tmp = nullptr;
+      size_t scan_bytes = 0;
+      cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, cnt, off, nt);
+      G(A(&cnt, (size_t)nt)) G(A(&off, (size_t)nt)) G(A((char **)&scan_tmp, scan_bytes))
+      double cell = std::cbrt(vol / (double)nt);
+      long long total = 0;
+      for (int it = 0; it < 40; ++it, cell *= 1.1225) {
+        k_presplit_count<<<(unsigned)((nt + 127) / 128), 128>>>(vx, vy, vz, idx, nt, cell, org[0], org[1], org[2], cnt);
+        cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, cnt, off, nt);
+        int last_off = 0, last_cnt = 0;
+        if (cudaMemcpy(&last_off, off + nt - 1, 4, cudaMemcpyDeviceToHost) != cudaSuccess ||
+            cudaMemcpy(&last_cnt, cnt + nt - 1, 4, cudaMemcpyDeviceToHost) != cudaSuccess) {
+          cleanup();
+          return fail(PTB_E_CUDA, "gpu build: pre-split count");
+        }
+        total = (long long)last_off + last_cnt;
+        if ((double)total <= f * (double)nt) break;
+      }
+      if (total > nt && total < (1 << 26)) {
+        float4 *rlo = nullptr, *rhi = nullptr;
+        G(A(&rlo, (size_t)total)) G(A(&rhi, (size_t)total)) G(A(&ref_tri, (size_t)total))
+        k_presplit_emit<<<(unsigned)((nt + 127) / 128), 128>>>(vx, vy, vz, idx, nt, cell, org[0], org[1], org[2], off, rlo, rhi, ref_tri);
+        G(H2D(cb, cb0, sizeof cb0))
+        k_box_bounds<<<(unsigned)((total + 255) / 256), 256>>>(rlo, rhi, (int)total, cb);
+        blo = rlo, bhi = rhi, n = (int)total;
+        if (std::getenv("PTB_BVH_TIMING"))
+          std::fprintf(stderr, "[gpu bvh] presplit: overlap %.2f, %d -> %d references, cell %.4g\n", hv / vol, nt, n, cell);
+      }
+    }
+  }
+  const bool sah = gpu_builder_sah();
+  const size_t nn = sah ? 2 * (size_t)n + 2 : (size_t)n;  // binary nodes
+  G(A(&nlo, nn)) G(A(&nhi, nn))
+  G(A(&k0, (size_t)n)) G(A(&k1, (size_t)n)) G(A(&v0, (size_t)n)) G(A(&v1, (size_t)n)) G(A(&visits, nn))
+  G(A(&lch, nn)) G(A(&rch, nn)) G(A(&first, nn)) G(A(&count, nn)) G(A(&pari, nn)) G(A(&parl, nn))
+  G(A(&counters, 4)) G(A(&fa, (size_t)n)) G(A(&fb, (size_t)n)) G(A(&tmp_nodes, (size_t)n))
+  (void)visits;
   const unsigned gb = (unsigned)((n + 255) / 256);
-  k_tri_boxes<<<gb, 256>>>(vx, vy, vz, idx, n, blo, bhi, cb);
   size_t cub_bytes = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, k0, k1, v0, v1, n, 0, 64);
   G(A((char **)&cub_tmp, cub_bytes))
@@ -933,7 +994,7 @@ static int gpu_build_mesh(ptb_scene *s) {
     cleanup();
     return fail(PTB_E_CUDA, "gpu build: copy failed");
   }
-  k_emit_tris<<<gb, 256>>>(v1, n, vx, vy, vz, idx, tmat, tuv, mkind, t.tris, t.tri_uv, d->tri_id, d->tri_mat, d->prim_kind);
+  k_emit_tris<<<gb, 256>>>(v1, n, ref_tri, vx, vy, vz, idx, tmat, tuv, mkind, t.tris, t.tri_uv, d->tri_id, d->tri_mat, d->prim_kind);
   std::vector<DTex<float>> texs(h.tex.size());
   for (size_t i = 0; i < texs.size(); ++i) {
     const ptb_texture &x = h.tex[i];
@@ -950,6 +1011,7 @@ static int gpu_build_mesh(ptb_scene *s) {
   WideBVH &b = s->bvh;
   b.nodes.clear(), b.sphere_order.clear(), b.tri_order.clear();
   b.device_built = true, b.dev_nodes = n_wide, b.dev_tris = n, b.dev_leaves = hc[2];
+  b.presplit = ref_tri != nullptr;
   b.depth = levels, b.max_stack = 3 * levels;
   return PTB_OK;
 }
@@ -1296,6 +1358,43 @@ int ptb_resolve_device(const float *d_sums, float *d_image, int32_t width, int32
   return resolve_impl<float, float>(d_sums, d_image, width, height, spp, flags, (cudaStream_t)stream);
 }
 
+// Caller-supplied rays -> the ray queue.  Scenes that are traversed in global memory get their rays in spatial order
+// (ray_sort.cuh); a scene staged in shared memory gains nothing from that (no memory system to be kind to) and keeps
+// the caller's order.  PTB_BATCH_SORT=0/1 overrides the choice (A/B measurements).
+static int pack_user_rays(DevicePool *pl, const ptb_scene *s, const DScene<float> &sc, const float *d_o, const float *d_d, long long m,
+                          float t_min, Queue<float> q, cudaStream_t st, uint64_t *launches) {
+  const char *e = std::getenv("PTB_BATCH_SORT");
+  const int env = e ? (std::atoi(e) != 0 ? 1 : 0) : 2;
+  // The sort costs about as much as tracing the batch against a few thousand primitives: it is for the scenes whose
+  // traversal is expensive and far-flung in memory — pre-split soups and meshes beyond the L2.
+  const bool heavy = s->bvh.presplit && (size_t)sc.n_tris * sizeof(TriG) + (size_t)sc.n_nodes * sizeof(NodeQ) > ((size_t)48 << 20);
+  const bool sorted = env == 2 ? (sc.scene_in_smem == 0 && heavy && m >= (1 << 15)) : env == 1;
+  const unsigned blocks = (unsigned)((m + 255) / 256);
+  if (!sorted || m <= 0) {
+    if (m > 0) k_pack_rays<float><<<blocks, 256, 0, st>>>(d_o, d_d, m, q);
+    *launches += 1;
+    return PTB_OK;
+  }
+  const size_t need = ray_sort_scratch_bytes((size_t)m);
+  if (pl->sort_cap < need) {
+    cudaFree(pl->sort_buf);
+    pl->sort_buf = nullptr, pl->sort_cap = 0;
+    CK(cudaMalloc(&pl->sort_buf, need));
+    pl->sort_cap = need;
+  }
+  unsigned *bins = (unsigned *)pl->sort_buf, *totals = bins + SORT_BINS, *keys = totals + SORT_SCAN_BLOCKS;
+  int oct_bits = 3;
+  if (const char *o = std::getenv("PTB_SORT_OCT")) oct_bits = std::atoi(o) ? 3 : 0;
+  const unsigned nbins = SORT_BINS >> (3 - oct_bits), scan_blocks = nbins / SORT_SCAN_TILE;
+  CK(cudaMemsetAsync(bins, 0, (size_t)nbins * 4, st));
+  k_ray_keys<<<blocks, 256, 0, st>>>(d_o, d_d, m, sc.nodes, t_min, oct_bits, keys, bins);
+  k_sort_scan_tiles<<<scan_blocks, SORT_SCAN_BLOCK, 0, st>>>(bins, totals);
+  k_sort_scan_add<<<scan_blocks, SORT_SCAN_BLOCK, 0, st>>>(bins, totals);
+  k_pack_rays_sorted<float><<<blocks, 256, 0, st>>>(d_o, d_d, m, keys, bins, q);
+  *launches += 4;
+  return PTB_OK;
+}
+
 int ptb_intersect_batch_device(ptb_scene *s, const float *d_o, const float *d_d, float t_min, float t_max,
                                int64_t n, float *d_t, int32_t *d_prim, int32_t device, void *stream,
                                ptb_stats *stats) {
@@ -1320,12 +1419,12 @@ int ptb_intersect_batch_device(ptb_scene *s, const float *d_o, const float *d_d,
   uint64_t launches = 0;
   for (int64_t first = 0; first < n; first += (int64_t)cap) {
     const long long m = std::min<int64_t>((int64_t)cap, n - first);
-    k_pack_rays<float><<<(unsigned)((m + 255) / 256), 256, 0, st>>>(d_o + 3 * first, d_d + 3 * first, m, w.rays);
+    if ((rc = pack_user_rays(pl, s, sc, d_o + 3 * first, d_d + 3 * first, m, t_min, w.rays, st, &launches))) return rc;
     CK(cudaMemsetAsync(&pl->ctl->cursor[MAX_BOUNCES], 0, sizeof(unsigned), st));
     launch_trace<float, 1>(tl, st, sc, nullptr, 0u, w.rays, nullptr, (unsigned)((m + SEG - 1) / SEG),
                            &pl->ctl->cursor[MAX_BOUNCES], w.mq, (unsigned)w.slots, nullptr, nullptr, 0, nullptr, t_min, t_max, d_t + first,
                            d_prim + first);
-    launches += 2;
+    launches += 1;
   }
   CK(cudaEventRecord(e1, st));
   CK(cudaGetLastError());
@@ -1434,14 +1533,14 @@ int ptb_intersect_batch(ptb_scene *s, const float *o, const float *dd, float t_m
     CK(cudaMemcpyAsync(d_d, dd + 3 * first, (size_t)m * 12, cudaMemcpyHostToDevice, st));
     // the ray queue and the claim cursor are shared by the two streams: the kernels of chunk k wait for chunk k-1's
     if (k > 0) CK(cudaStreamWaitEvent(st, S.traced[(k - 1) % nbuf], 0));
-    k_pack_rays<float><<<(unsigned)((m + 255) / 256), 256, 0, st>>>(d_o, d_d, m, w.rays);
+    if ((rc = pack_user_rays(pl, s, sc, d_o, d_d, m, t_min, w.rays, st, &launches))) return rc;
     CK(cudaMemsetAsync(&pl->ctl->cursor[MAX_BOUNCES], 0, sizeof(unsigned), st));
     launch_trace<float, 1>(tl, st, sc, nullptr, 0u, w.rays, nullptr, (unsigned)((m + SEG - 1) / SEG),
                            &pl->ctl->cursor[MAX_BOUNCES], w.mq, (unsigned)w.slots, nullptr, nullptr, 0, nullptr, t_min, t_max, d_t, d_p);
     CK(cudaEventRecord(S.traced[b], st));
     CK(cudaMemcpyAsync(t_hit + first, d_t, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(prim + first, d_p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
-    launches += 2;
+    launches += 1;
   }
   CK(cudaGetLastError());
   for (int i = 0; i < nbuf; ++i) CK(cudaStreamSynchronize(S.st[i]));

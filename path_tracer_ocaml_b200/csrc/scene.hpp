@@ -57,6 +57,7 @@ struct WideBVH {
   std::vector<int32_t> tri_order;     // device slot -> triangle index as set by the caller
   int depth = 0;                   // inner levels
   int max_stack = 0;               // worst-case traversal stack entries
+  bool presplit = false;           // triangle slots are REFERENCES (presplit.hpp): a triangle may occupy several slots
   // tree built on the device (gpu_bvh.cuh): `nodes` / `tri_order` stay empty, only the counts are known here
   bool device_built = false;
   int64_t dev_nodes = 0, dev_tris = 0, dev_leaves = 0;
