@@ -67,6 +67,14 @@ PTB_HD void box_of(const Poly &p, double lo[3], double hi[3]) {
 // h: cell size; org: origin of the grid hierarchy (any fixed point, e.g. the scene's lower corner).
 template <class Emit>
 PTB_HD int pieces(const double v[3][3], double h, const double org[3], Emit &&emit) {
+  // One triangle never becomes more than a few dozen pieces: a triangle much longer than the cell (a ground plane under
+  // a soup) is cut on a coarser level of the same grid hierarchy, at most 8 cells along its longest side.
+  {
+    double e = 0.0;
+    for (int a = 0; a < 3; ++a) e = fmax(e, fmax(fmax(v[0][a], v[1][a]), v[2][a]) - fmin(fmin(v[0][a], v[1][a]), v[2][a]));
+    for (int k = 0; k < 60 && e > 8.0 * h; ++k) h *= 2.0;
+  }
+  const double finest = h * (1.0 / 64.0);
   int count = 0;
   uint32_t path = 0;  // bit d: the turn taken at depth d (0 = lower side)
   int depth = 0;      // turns of `path` that are fixed; below them the enumeration keeps to the lower side
@@ -87,7 +95,7 @@ PTB_HD int pieces(const double v[3][3], double h, const double org[3], Emit &&em
       if (!(ext > h) || d >= MAX_DEPTH) break;  // a piece
       // the coarsest plane of the grid hierarchy strictly inside the box (the midpoint if rounding hides them all)
       double pos = 0.5 * (lo[ax] + hi[ax]);
-      for (double s = h * 1048576.0; s >= h * (1.0 / 64.0); s *= 0.5) {
+      for (double s = h * 1048576.0; s >= finest; s *= 0.5) {
         double c = (floor((lo[ax] - org[ax]) / s) + 1.0) * s + org[ax];  // the first plane above the lower face
         if (!(c > lo[ax] + 1e-9 * s)) c += s;
         if (c < hi[ax] - 1e-9 * s) {

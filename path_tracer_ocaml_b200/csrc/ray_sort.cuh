@@ -4,10 +4,10 @@
 // node and triangle record is a separate L1 wavefront and mostly an L2 round trip ("global-memory
 // scenes").  The reference's FFI contract (sphere-intersect-rs/src/lib.rs:53-76) only fixes that result i belongs to ray
 // i, so the rays are put into the traversal queue in SPATIAL order instead — a counting sort on
-//   key = Morton code of the cell (64^3 over the scene's box) where the ray enters the scene | direction octant
-// — and every queue entry carries the caller's index of its ray (A.w), which is where k_trace<MODE 1> writes the
-// result.  Four small kernels, all bound by HBM traffic (28 B read + 4 B written per ray for the keys, 28 B read + 32 B
-// written for the scatter) and two orders of magnitude cheaper than the traversal they speed up.
+//   key = Morton code of the cell (64^3 over the scene's box) where the ray enters the scene
+// (optionally | direction octant: PTB_SORT_OCT=1, measured slower) — and every queue entry carries the caller's index of its ray (A.w), which is where k_trace<MODE 1> writes the
+// result.  Five small kernels (keys + histogram, two for the scan of the bins, index scatter, gather into the queue),
+// bound by memory traffic and together well over an order of magnitude cheaper than the traversal they speed up.
 #pragma once
 #include <cstdint>
 
@@ -23,8 +23,8 @@ constexpr unsigned SORT_SCAN_BLOCKS = SORT_BINS / SORT_SCAN_TILE;            // 
 static_assert(SORT_BINS % SORT_SCAN_TILE == 0 && SORT_SCAN_BLOCKS <= 1024, "scan shape");
 // (with oct_bits = 0 the key is the cell alone: 2^18 bins, 128 blocks of the scan)
 
-// bytes of scratch the sort of m rays needs: keys, bin counters, per-block totals of the scan
-static inline size_t ray_sort_scratch_bytes(size_t m) { return m * 4 + (size_t)SORT_BINS * 4 + SORT_SCAN_BLOCKS * 4; }
+// bytes of scratch the sort of m rays needs: keys, permutation, bin counters, per-block totals of the scan
+static inline size_t ray_sort_scratch_bytes(size_t m) { return 2 * m * 4 + (size_t)SORT_BINS * 4 + SORT_SCAN_BLOCKS * 4; }
 
 __device__ __forceinline__ unsigned spread3(unsigned v) {  // 6 bits -> every third bit
   v = (v | (v << 8)) & 0x0300F00Fu;
@@ -117,17 +117,26 @@ __global__ void __launch_bounds__(SORT_SCAN_BLOCK) k_sort_scan_add(unsigned *__r
   p[0] = a, p[1] = b;
 }
 
-// user rays (3 floats each) -> ray queue, ray i into the slot its key's bin hands out; A.w = i
-template <class R>
-__global__ void __launch_bounds__(256) k_pack_rays_sorted(const float *__restrict__ o, const float *__restrict__ d, long long n,
-                                                          const unsigned *__restrict__ keys, unsigned *__restrict__ bins, Queue<R> q) {
+// The scatter moves only the ray's INDEX (4 bytes into a table that stays in the L2); the rays themselves are then
+// gathered slot by slot, so that the queue is written in full, consecutive sectors.  (Scattering the 32 bytes of a ray
+// as two 16-byte halves of 32-byte sectors was measured at 190 us per 4 Mi rays: every one of them a read-modify-write.)
+__global__ void __launch_bounds__(256) k_sort_scatter(long long n, const unsigned *__restrict__ keys, unsigned *__restrict__ bins,
+                                                      unsigned *__restrict__ perm) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const unsigned slot = atomicAdd(&bins[keys[i]], 1u);
-  Vec4<R> *e = q.A(slot);
+  perm[atomicAdd(&bins[keys[i]], 1u)] = (unsigned)i;
+}
+// user rays (3 floats each) -> ray queue: slot s takes ray perm[s]; A.w = the caller's index of that ray
+template <class R>
+__global__ void __launch_bounds__(256) k_pack_rays_sorted(const float *__restrict__ o, const float *__restrict__ d, long long n,
+                                                          const unsigned *__restrict__ perm, Queue<R> q) {
+  const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const size_t i = perm[s];
+  Vec4<R> *e = q.A((unsigned)s);
   e[0] = {R(o[3 * i]), R(o[3 * i + 1]), R(o[3 * i + 2]), i2r((int)i, R())};
   e[SEG] = {R(d[3 * i]), R(d[3 * i + 1]), R(d[3 * i + 2]), R(0)};
-  if (i % SEG == 0) q.seg_count[i / SEG] = (int32_t)(n - i < SEG ? n - i : SEG);  // dense
+  if (s % SEG == 0) q.seg_count[s / SEG] = (int32_t)(n - s < SEG ? n - s : SEG);  // dense
 }
 
 }  // namespace ptb

@@ -201,7 +201,11 @@ def sweep(quick):
                 row = {"prims": kind, "m": m, "rays": n, "coherent": coherent, "commit_ms": commit_ms,
                        "gpu_mrays_per_s_device": m_dev / dev_ms / 1e3, "device_rays": m_dev,
                        "gpu_mrays_per_s_host_buffers": n / host_ms / 1e3, "host_buffers": "page-locked (ptb_host_alloc), chunk-pipelined",
-                       "hit_fraction": float(np.mean(p[:base] >= 0))}
+                       "hit_fraction": float(np.mean(p[:base] >= 0)), "tree": s.tree_stats()}
+                if kind == "triangles" and row["tree"]["triangles"] > m:
+                    row["tree_note"] = ("pre-split soup (csrc/presplit.hpp): the tree holds several box references per triangle and the rays "
+                                        "are traced in spatial order (csrc/ray_sort.cuh, inside the timed region); the roofline's work per ray is "
+                                        "counted on the reference's tree, one box per triangle, which this tree undercuts")
                 if osc is not None:
                     # CPU side on a bounded sample: the oracle's reference-faithful tree + leaf kernels
                     ns = min(n, 1 << 18)
