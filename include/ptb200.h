@@ -151,13 +151,15 @@ int ptb_scene_set_background(ptb_scene *, int32_t kind, const double c0[3], cons
  * the parallelogram origin + a*u + b*v, a, b in [0,1], in camera space; the emitting geometry itself is ordinary
  * triangles with a PTB_MAT_EMISSIVE material.  NULL origin removes the light (back to `Pdf.diffuse`). */
 int ptb_scene_set_light_quad(ptb_scene *, const double origin[3], const double u[3], const double v[3]);
-/* Shape_tree.create (path_tracer/src/shape_tree.ml:252-263): builds the tree on the host and
- * uploads it to `device`.  Returns build+upload milliseconds through *ms if non-NULL. */
+/* Shape_tree.create (path_tracer/src/shape_tree.ml:252-263): builds the tree (on the host, or on the device for
+ * pure triangle meshes of >= 200 k triangles) and uploads it to `device`.  Returns build+upload milliseconds through *ms if non-NULL. */
 int ptb_scene_commit(ptb_scene *, int32_t device, double *ms);
 int64_t ptb_scene_primitive_count(const ptb_scene *);
 /* Shape of the committed device tree (the reference prints depth and a leaf-length histogram,
  * shirley_spheres/bin/main.ml:263-267): out = {wide nodes, depth, worst-case stack entries, spheres,
- * triangles, leaves, max leaf size, 0}. */
+ * triangle slots, leaves, max leaf size, 0}.  Triangle slots = triangles, except for soups of overlapping triangles,
+ * which the builders pre-split (csrc/presplit.hpp): then a triangle occupies one slot per box reference;
+ * ptb_scene_primitive_count still counts the caller's shapes, and hits always name the caller's triangle. */
 int ptb_scene_tree_stats(const ptb_scene *, int32_t out[8]);
 
 /* Integrator.render (integrator.ml:130-156) with HOST image: `image_rgb` is 3*W*H doubles laid out
@@ -194,7 +196,9 @@ int ptb_resolve_device(const float *d_sums, float *d_image, int32_t width, int32
 /* Batched generalisation of spheres_intersect_native (lib.rs:53-76): n rays against the committed
  * scene; origins/directions are 3*n floats (x,y,z interleaved); writes nearest t (NaN on miss, as
  * the reference initialises t_hit_ref, main.ml:207) and primitive index (-1 on miss, lib.rs:74;
- * spheres first then triangles, in the order they were set). */
+ * spheres first then triangles, in the order they were set).  The library may trace the rays in another
+ * order than the caller's (csrc/ray_sort.cuh: spatial order on big triangle soups); result i always belongs to ray i
+ * and does not depend on that order. */
 int ptb_intersect_batch(ptb_scene *, const float *origins, const float *directions, float t_min,
                         float t_max, int64_t n, float *t_hit, int32_t *prim, int32_t device,
                         ptb_stats *);
