@@ -261,7 +261,7 @@ static double presplit_triangles(const HostScene &s, std::vector<PrimRef> &tri, 
   for (int it = 0; it < 40 && (double)run(h, nullptr) > max_factor * (double)n; ++it) h *= 1.1225;
   std::vector<PrimRef> refs;
   run(h, &refs);
-  tri.swap(refs);
+  if (refs.size() < ((size_t)1 << 26)) tri.swap(refs);  // (a leaf code addresses 2^26 slots; beyond that the triangles stay whole)
   return h;
 }
 

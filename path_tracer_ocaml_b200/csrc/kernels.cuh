@@ -1070,6 +1070,9 @@ __global__ void __launch_bounds__(256) k_raygen(GenConst g, unsigned n, Queue<R>
 // Incoming rays never wait on HBM/L2: each warp keeps the next RING entries (origin, direction) of its claimed
 // chunk in flight into its staging ring (cp.async issued one refill ahead), and the payload of a ray goes
 // straight from the queue into the lane's payload slot (cp.async, first read at the lane's flush).
+#ifndef PTB_LEAF_MIN_G
+#define PTB_LEAF_MIN_G 8  // the same threshold for scenes in global memory (phase loops)
+#endif
 constexpr int LEAF_MIN = 8;  // lanes holding a leaf before the warp runs the leaf phase (tuned: 6..12 equal, 1: -4 %;
                              // global-memory triangle scenes measured with 8 / 12 / 16 / 20 / 24: best at 8..12)
 constexpr unsigned WS_NEXT = 0, WS_END = 1, WS_FETCHED = 2, WS_SEG = 3 /* base,fill x 3 kinds */, WS_STAGED = 9,
@@ -1462,7 +1465,7 @@ __global__ void __launch_bounds__(SMEM ? (sizeof(R) == 8 ? 512 : 1024) : 256, SM
       }
       const bool at_leaf = (unsigned)(L.cur - (TRAV_POP + 1)) < (unsigned)(0 - (TRAV_POP + 1));  // TRAV_POP < cur < 0
       const unsigned lm = __ballot_sync(0xffffffffu, at_leaf);
-      if (__popc(lm) >= LEAF_MIN || lm == act) {  // (lm == 0 never equals act inside the loop)
+      if (__popc(lm) >= (SMEM ? LEAF_MIN : PTB_LEAF_MIN_G) || lm == act) {  // (lm == 0 never equals act inside the loop)
         if (at_leaf) leaf_phase<R, SMEM, MODE == 0, UNIT>(L, S);
       }
       if (L.cur == TRAV_POP) pop_phase<R, !SMEM>(L, K);

@@ -857,9 +857,10 @@ static int gpu_build_mesh(ptb_scene *s) {
       size_t scan_bytes = 0;
       cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, cnt, off, nt);
       G(A(&cnt, (size_t)nt)) G(A(&off, (size_t)nt)) G(A((char **)&scan_tmp, scan_bytes))
-      double cell = std::cbrt(vol / (double)nt);
+      double cell = std::cbrt(vol / (double)nt), next_cell = cell;
       long long total = 0;
-      for (int it = 0; it < 40; ++it, cell *= 1.1225) {
+      for (int it = 0; it < 40; ++it, next_cell *= 1.1225) {
+        cell = next_cell;  // (the cell size the counts and offsets below belong to: k_presplit_emit must use the same)
         k_presplit_count<<<(unsigned)((nt + 127) / 128), 128>>>(vx, vy, vz, idx, nt, cell, org[0], org[1], org[2], cnt);
         cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, cnt, off, nt);
         int last_off = 0, last_cnt = 0;
