@@ -305,13 +305,14 @@ void build_wide_bvh(const HostScene &s, WideBVH *out) {
     // how many triangle boxes contain a random point of the scene (presplit.hpp: far below 1 for surface meshes)
     Box all;
     all.reset();
-    double vsum = 0.0;
-    for (const PrimRef &p : tri) {
-      all.grow(p.box);
-      vsum += (p.box.mx[0] - p.box.mn[0]) * (p.box.mx[1] - p.box.mn[1]) * (p.box.mx[2] - p.box.mn[2]);
-    }
+    for (const PrimRef &p : tri) all.grow(p.box);
     double vol = 1.0;
     for (int a = 0; a < 3; ++a) vol *= std::max(all.mx[a] - all.mn[a], 1e-12);
+    // (one box counts for at most 64 mean cells: a tilted ground plane under a mesh must not pass for a soup)
+    const double vcap = presplit::OVERLAP_BOX_CAP * vol / (double)tri.size();
+    double vsum = 0.0;
+    for (const PrimRef &p : tri)
+      vsum += std::min(vcap, (p.box.mx[0] - p.box.mn[0]) * (p.box.mx[1] - p.box.mn[1]) * (p.box.mx[2] - p.box.mn[2]));
     double f = presplit::budget_factor(vsum / vol);
     if (const char *e = std::getenv("PTB_BVH_PRESPLIT")) f = std::atof(e);  // 0 / 1: off; > 1: references per triangle allowed
     // (small scenes are traversed out of shared memory and must stay small)

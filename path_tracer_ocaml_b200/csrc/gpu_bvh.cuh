@@ -78,10 +78,10 @@ __global__ void __launch_bounds__(256) k_tri_boxes(const double *__restrict__ vx
 // 1b. triangle pre-splitting (presplit.hpp): how many boxes contain a random point (the trigger), pieces per triangle
 // for a cell size, and the pieces' boxes as the builder's primitives
 __global__ void __launch_bounds__(256) k_box_volume_sum(const float4 *__restrict__ blo, const float4 *__restrict__ bhi, int n,
-                                                        double *__restrict__ sum) {
+                                                        double cap, double *__restrict__ sum) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   double v = 0.0;
-  if (i < n) v = (double)(bhi[i].x - blo[i].x) * (double)(bhi[i].y - blo[i].y) * (double)(bhi[i].z - blo[i].z);
+  if (i < n) v = fmin(cap, (double)(bhi[i].x - blo[i].x) * (double)(bhi[i].y - blo[i].y) * (double)(bhi[i].z - blo[i].z));
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   if ((threadIdx.x & 31) == 0 && v > 0.0) atomicAdd(sum, v);
 }

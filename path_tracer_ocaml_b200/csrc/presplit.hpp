@@ -142,7 +142,10 @@ PTB_HD int pieces(const double v[3][3], double h, const double org[3], Emit &&em
 
 // Pre-split when the boxes of the triangles overlap: `overlap` = sum of the box volumes / volume of the scene's box =
 // how many boxes contain a random point.  Surface meshes are far below 1, soups of big triangles far above.
+// A single box enters the sum with at most OVERLAP_BOX_CAP mean cells (scene volume / triangles), so that a few huge
+// triangles — a tilted ground plane under a mesh — do not make a surface look like a soup.
 // Returns the references per triangle the builder may spend (1 = leave the triangles whole).
+constexpr double OVERLAP_BOX_CAP = 64.0;
 PTB_HD double budget_factor(double overlap) { return overlap <= 0.5 ? 1.0 : (overlap >= 5.0 ? 6.0 : 1.0 + overlap); }
 
 }  // namespace presplit

@@ -837,10 +837,9 @@ static int gpu_build_mesh(ptb_scene *s) {
       cleanup();
       return fail(PTB_E_CUDA, "gpu build: memset failed");
     }
-    k_box_volume_sum<<<(unsigned)((nt + 255) / 256), 256>>>(blo, bhi, nt, vsum);
     Bounds6 hb[2];
     double hv = 0.0;
-    if (cudaMemcpy(hb, cb, sizeof hb, cudaMemcpyDeviceToHost) != cudaSuccess || cudaMemcpy(&hv, vsum, 8, cudaMemcpyDeviceToHost) != cudaSuccess) {
+    if (cudaMemcpy(hb, cb, sizeof hb, cudaMemcpyDeviceToHost) != cudaSuccess) {
       cleanup();
       return fail(PTB_E_CUDA, "gpu build: box bounds");
     }
@@ -848,6 +847,11 @@ static int gpu_build_mesh(ptb_scene *s) {
     for (int k = 0; k < 3; ++k) {
       org[k] = (double)dec_f(hb[1].lo[k]);
       vol *= std::max((double)dec_f(hb[1].hi[k]) - org[k], 1e-12);
+    }
+    k_box_volume_sum<<<(unsigned)((nt + 255) / 256), 256>>>(blo, bhi, nt, presplit::OVERLAP_BOX_CAP * vol / (double)nt, vsum);
+    if (cudaMemcpy(&hv, vsum, 8, cudaMemcpyDeviceToHost) != cudaSuccess) {
+      cleanup();
+      return fail(PTB_E_CUDA, "gpu build: box volumes");
     }
     double f = presplit::budget_factor(hv / vol);
     if (const char *e = std::getenv("PTB_BVH_PRESPLIT")) f = std::atof(e);  // 0 / 1: off; > 1: references per triangle allowed

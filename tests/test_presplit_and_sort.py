@@ -173,3 +173,34 @@ def test_render_of_a_presplit_soup_matches_oracle(monkeypatch):
     d = img - ref
     assert np.sqrt(np.mean(d * d)) <= 0.01
     assert abs(int(integ.stats.rays) - int(cn.rays)) / cn.rays < 2e-3
+
+
+@pytest.mark.gpu
+def test_a_surface_with_a_tilted_ground_plane_is_not_taken_for_a_soup(monkeypatch):
+    """The pre-split trigger counts how many triangle boxes contain a random point, every box capped at 64 mean cells:
+    a wavy surface mesh stays one box per triangle even with two huge tilted triangles under it, whose boxes alone
+    fill the scene; the hits equal the oracle's either way."""
+    monkeypatch.delenv("PTB_BVH_PRESPLIT", raising=False)
+    g = 80
+    u, v = np.meshgrid(np.linspace(-5, 5, g + 1), np.linspace(-5, 5, g + 1), indexing="ij")
+    z = 0.3 * np.sin(1.7 * u) * np.cos(1.3 * v)
+    verts = np.stack([u.ravel(), v.ravel(), z.ravel()], 1)
+    q = (np.arange(g)[:, None] * (g + 1) + np.arange(g)[None, :]).ravel()
+    faces = np.concatenate([np.stack([q, q + 1, q + g + 2], 1), np.stack([q, q + g + 2, q + g + 1], 1)])
+    nv = len(verts)
+    ground = np.array([[-6, -6, -3.0], [6, -6, -1.0], [6, 6, 1.0], [-6, 6, -1.0]])  # tilted: its triangles' boxes span the scene
+    verts = np.concatenate([verts, ground])
+    faces = np.concatenate([faces, [[nv, nv + 1, nv + 2], [nv, nv + 2, nv + 3]]]).astype(np.int32)
+    m = len(faces)
+    assert m >= 4096
+    s = P.Scene()
+    s.set_textures([capi.Texture(kind=capi.PTB_TEX_SOLID, rgb=(0.5, 0.5, 0.5))])
+    s.set_materials([capi.Material(kind=capi.PTB_MAT_LAMBERTIAN, texture=0, index=1.0)])
+    s.set_triangles(verts[:, 0], verts[:, 1], verts[:, 2], faces)
+    s.set_background(capi.PTB_BG_CONSTANT, (1.0, 1.0, 1.0))
+    s.commit(0)
+    assert s.tree_stats()["triangles"] == m
+    o, d = _rays(50_000, 5.0, 21)
+    t, p = integrator.intersect_batch(s, o, d)
+    tr, pr, _ = O.OracleScene(s.tables()).intersect_batch(o.astype(np.float64), d.astype(np.float64), n_threads=NCPU)
+    assert (p == pr).mean() >= 0.999 and (pr >= 0).mean() > 0.2
