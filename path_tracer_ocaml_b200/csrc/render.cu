@@ -453,13 +453,20 @@ static int trace_config(DeviceState *d, const DScene<R> &sc, size_t scene_bytes,
   }
   return PTB_OK;
 }
-static int refill_below() {
-  static int v = -1;
-  if (v < 0) {
-    v = 10;  // measured flat between 8 and 14, slower above (also for global-memory triangle scenes: 12..28 within 4 %)
-    if (const char *e = std::getenv("PTB_REFILL")) v = std::min(32, std::max(1, std::atoi(e)));
+// A warp flushes its finished lanes and refills them when fewer than this many lanes are still traversing.
+static int refill_below(bool scene_smem, bool batch_mode) {
+  static int env = -2;
+  if (env == -2) {
+    env = -1;
+    if (const char *e = std::getenv("PTB_REFILL")) env = std::min(32, std::max(1, std::atoi(e)));
   }
-  return v;
+  if (env > 0) return env;
+  // Render pipeline and scenes in shared memory: measured flat between 8 and 14, slower above (a flush + refill of the
+  // render pipeline is ~200 instructions per warp; the C3 mesh renders lose 5-7 % at 26).  ptb_intersect_batch on a
+  // scene in global memory: every traversal step waits on a gather, the flush is two stores, idle lanes are what costs:
+  // refilling below 26 lanes gives +16 % / +21 % on 10^5 / 10^4 triangles, +13-18 % on 4096 spheres and +3 % on the
+  // pre-split 10^6 soup (incoherent rays).
+  return (!scene_smem && batch_mode) ? 26 : 10;
 }
 // gen != nullptr: bounce 0, the kernel generates the camera rays [0, gen_n) of the batch itself
 template <class R, int MODE>
@@ -472,7 +479,7 @@ static void launch_trace(const TraceLaunch &tl, cudaStream_t st, const DScene<R>
   if (gen) g = *gen;
 #define PTB_LAUNCH(SM, GN, BK)                                                                                         \
   k_trace<R, MODE, SM, GN, BK><<<tl.grid, tl.block, tl.smem, st>>>(sc, g, gen_n, rays, nseg_ptr, nseg_imm, cursor,    \
-                                                                   refill_below(), mq, mq_slots, nseg_mat,                \
+                                                                   refill_below(tl.scene_smem, MODE == 1), mq, mq_slots, nseg_mat,                \
                                                                    n_traced, enqueue_hits, sums, tmin, tmax, out_t, out_prim)
   constexpr int FIXED = sizeof(R) == 4 ? 1024 : 0;  // float, shared-memory scene, full block: compile-time block size
   const bool fixed = FIXED != 0 && tl.scene_smem && tl.block == 1024;
